@@ -1,0 +1,16 @@
+"""flow-pipeline_b200 -- B200-native flow-aggregation stage (drop-in for the
+decode->aggregate path of cloudflare/flow-pipeline).
+
+The package holds only what that path needs:
+  csrc/         the sm_100a CUDA kernels and the C ABI (include/flowagg.h)
+  flowagg.py    ctypes binding of libflowagg.so (what the tests and bench.py drive)
+  inserter.py   host-side mirror of inserter/inserter.go's consumer-group handler
+
+The directory name contains a hyphen (it mirrors the reference's name), so
+import it with importlib.import_module("flow-pipeline_b200") or through the
+flow_pipeline_b200 shim module at the repository root.
+"""
+from .flowagg import (  # noqa: F401
+    FaConfig, FaMockerConfig, FlowAgg, FlowAggError, KEY_MODES, KEY_WORDS, ROW_DTYPE, HH_DTYPE,
+    build, lib_path, load_library, mocker_host,
+)

@@ -1,0 +1,936 @@
+// flowagg.cu -- implementation of the C ABI in include/flowagg.h.
+//
+// Host side of the B200-native replacement for (*state).buffer / (*state).flush
+// (inserter/inserter.go:90-165) and the flows_5m roll-up
+// (compose/clickhouse/create.sh:92-110).  All compute is in the sm_100a kernels
+// of kernels.cuh; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#define FA_STR2(x) #x
+#define FA_STR(x) FA_STR2(x)
+#define FA_STR_CUDART FA_STR(CUDART_VERSION)
+
+#include "../../include/flowagg.h"
+#include "kernels.cuh"
+#include "mocker_gen.h"
+
+using namespace fa;
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+
+struct fa_ctx {
+    fa_config cfg;
+    int kw = 0;
+    uint32_t slot_bytes = 0;
+    uint64_t capacity = 0;
+    bool weighted = false;
+
+    cudaStream_t stream = nullptr;  // compute
+    cudaStream_t copy_stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+
+    uint8_t *d_slots = nullptr;
+    unsigned long long *d_cms = nullptr, *d_cms_global = nullptr;
+    size_t cms_words = 0;
+    Counters *d_counters = nullptr;
+    Counters *h_counters = nullptr;  // pinned
+
+    // host-submit staging (double buffered)
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    uint32_t *d_stage_off[2] = {nullptr, nullptr};
+    cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    int next_stage = 0;
+    uint8_t *h_slab[2] = {nullptr, nullptr};
+    uint32_t *h_slab_off[2] = {nullptr, nullptr};
+    cudaEvent_t ev_slab[2] = {nullptr, nullptr};
+    uint32_t *d_frame_off = nullptr;  // offsets found on the GPU (offsets == NULL submits)
+    size_t frame_off_cap = 0;
+
+    // kernel-1 columns of the last submit
+    Columns cols{};
+    uint64_t cols_n = 0;
+    void *cols_block = nullptr;
+
+    // flush / top-K scratch
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+
+    uint64_t n_records = 0, n_submits = 0, bytes_in = 0;
+    std::string last_error;
+};
+
+#define FA_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            (ctx)->last_error = b__;                                                               \
+            return FA_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+static const int k_key_words[FA_KEY_MODES] = {4, 2, 4, 4, 11, 1, 1};
+
+static uint32_t slot_bytes_for(int kw) { return ((4u + 4u * (uint32_t)kw + 7u) & ~7u) + 24u; }
+
+extern "C" const char *fa_strerror(int s)
+{
+    switch (s) {
+    case FA_OK: return "ok";
+    case FA_ERR_INVALID: return "invalid argument";
+    case FA_ERR_CUDA: return "CUDA error";
+    case FA_ERR_NOMEM: return "out of memory";
+    case FA_ERR_CAPACITY: return "output capacity too small";
+    case FA_ERR_TABLE_FULL: return "group table full";
+    case FA_ERR_NCCL: return "NCCL error";
+    case FA_ERR_FRAMING: return "stream ends inside a record";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *fa_last_error(const fa_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+extern "C" const char *fa_build_info(void) { return "libflowagg abi=1 arch=sm_100a cuda=" FA_STR_CUDART; }
+
+static int ensure_scratch(fa_ctx *c, size_t bytes)
+{
+    if (bytes <= c->scratch_bytes) return FA_OK;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    FA_CUDA(c, cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return FA_OK;
+}
+
+extern "C" void fa_destroy(fa_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->d_slots);
+    cudaFree(c->d_cms);
+    cudaFree(c->d_cms_global);
+    cudaFree(c->d_counters);
+    cudaFreeHost(c->h_counters);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_stage[i]);
+        cudaFree(c->d_stage_off[i]);
+        cudaFreeHost(c->h_slab[i]);
+        cudaFreeHost(c->h_slab_off[i]);
+        if (c->ev_staged[i]) cudaEventDestroy(c->ev_staged[i]);
+        if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+        if (c->ev_slab[i]) cudaEventDestroy(c->ev_slab[i]);
+    }
+    cudaFree(c->d_frame_off);
+    cudaFree(c->cols_block);
+    cudaFree(c->d_scratch);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int alloc_columns(fa_ctx *c)
+{
+    const size_t n = c->cfg.max_batch_records;
+    // one block: 5 u64, 8 u32, 3 x 16 B, 4 u8 columns
+    const size_t bytes = n * (5 * 8 + 8 * 4 + 3 * 16 + 4) + 1024;
+    FA_CUDA(c, cudaMalloc(&c->cols_block, bytes));
+    uint8_t *p = (uint8_t *)c->cols_block;
+    auto take = [&](size_t b) { uint8_t *r = p; p += (b + 255) & ~(size_t)255; return r; };
+    Columns &k = c->cols;
+    k.src_addr = (uint4 *)take(n * 16);
+    k.dst_addr = (uint4 *)take(n * 16);
+    k.sampler_addr = (uint4 *)take(n * 16);
+    k.time_received = (unsigned long long *)take(n * 8);
+    k.time_flow_start = (unsigned long long *)take(n * 8);
+    k.sampling_rate = (unsigned long long *)take(n * 8);
+    k.bytes = (unsigned long long *)take(n * 8);
+    k.packets = (unsigned long long *)take(n * 8);
+    k.type = (uint32_t *)take(n * 4);
+    k.sequence_num = (uint32_t *)take(n * 4);
+    k.src_as = (uint32_t *)take(n * 4);
+    k.dst_as = (uint32_t *)take(n * 4);
+    k.etype = (uint32_t *)take(n * 4);
+    k.proto = (uint32_t *)take(n * 4);
+    k.src_port = (uint32_t *)take(n * 4);
+    k.dst_port = (uint32_t *)take(n * 4);
+    k.valid = take(n);
+    k.src_addr_len = take(n);
+    k.dst_addr_len = take(n);
+    k.sampler_addr_len = take(n);
+    return FA_OK;
+}
+
+extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
+{
+    if (!cfg || !out || cfg->abi_version != FA_ABI_VERSION) return FA_ERR_INVALID;
+    if (cfg->key_mode >= FA_KEY_MODES) return FA_ERR_INVALID;
+    if ((cfg->flags & FA_CFG_NO_AGGREGATE) && !(cfg->flags & FA_CFG_COLUMNS)) return FA_ERR_INVALID;
+    fa_ctx *c = new (std::nothrow) fa_ctx();
+    if (!c) return FA_ERR_NOMEM;
+    *out = c;  // returned even on failure so the caller can read fa_last_error, then fa_destroy
+    c->cfg = *cfg;
+    if (!c->cfg.table_capacity) c->cfg.table_capacity = 1ull << 17;
+    if (!c->cfg.cms_depth) c->cfg.cms_depth = 4;
+    if (!c->cfg.cms_width_log2) c->cfg.cms_width_log2 = 20;
+    if (!c->cfg.max_batch_bytes) c->cfg.max_batch_bytes = 256ull << 20;
+    if (!c->cfg.max_batch_records) c->cfg.max_batch_records = 4u << 20;
+    if (c->cfg.cms_depth > 16 || c->cfg.cms_width_log2 > 30 || c->cfg.cms_width_log2 < 4) return FA_ERR_INVALID;
+    if (c->cfg.max_batch_bytes > 0xFFFFFFF0ull) return FA_ERR_INVALID;  // offsets are u32
+    uint64_t cap = 16;
+    while (cap < c->cfg.table_capacity) cap <<= 1;
+    if (cap > (1ull << 32)) return FA_ERR_INVALID;
+    c->capacity = cap;
+    c->kw = k_key_words[c->cfg.key_mode];
+    c->slot_bytes = slot_bytes_for(c->kw);
+    c->weighted = (c->cfg.flags & (FA_CFG_CMS | FA_CFG_SCALE_SAMPLING)) != 0;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        c->last_error = "no CUDA device: libflowagg has no CPU fallback";
+        return FA_ERR_CUDA;
+    }
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaDeviceProp prop;
+    FA_CUDA(c, cudaGetDeviceProperties(&prop, c->cfg.device));
+    if (prop.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "device %d is sm_%d%d; libflowagg carries sm_100a code only", c->cfg.device, prop.major, prop.minor);
+        c->last_error = b;
+        return FA_ERR_CUDA;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if (c->cfg.stream) {
+        c->stream = (cudaStream_t)c->cfg.stream;
+    } else {
+        FA_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    FA_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    FA_CUDA(c, cudaEventCreate(&c->ev_t0));
+    FA_CUDA(c, cudaEventCreate(&c->ev_t1));
+    for (int i = 0; i < 2; i++) {
+        FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_staged[i], cudaEventDisableTiming));
+        FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+        FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_slab[i], cudaEventDisableTiming));
+    }
+    FA_CUDA(c, cudaMalloc(&c->d_counters, sizeof(Counters)));
+    FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
+    if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
+        FA_CUDA(c, cudaMalloc(&c->d_slots, c->capacity * c->slot_bytes));
+        FA_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->capacity * c->slot_bytes, c->stream));
+    }
+    if (c->cfg.flags & FA_CFG_CMS) {
+        c->cms_words = (size_t)c->cfg.cms_depth << c->cfg.cms_width_log2;
+        FA_CUDA(c, cudaMalloc(&c->d_cms, c->cms_words * 8));
+        FA_CUDA(c, cudaMemsetAsync(c->d_cms, 0, c->cms_words * 8, c->stream));
+    }
+    if (c->cfg.flags & FA_CFG_COLUMNS) {
+        int rc = alloc_columns(c);
+        if (rc) return rc;
+    }
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel launch
+// ---------------------------------------------------------------------------------------------
+
+template <int MODE>
+static cudaError_t launch_fused_mode(fa_ctx *c, const SubmitParams &p, uint32_t n_tiles, int grid, size_t smem)
+{
+    if (c->weighted) k_decode_aggregate<MODE, true><<<grid, kThreads, smem, c->stream>>>(p, n_tiles);
+    else k_decode_aggregate<MODE, false><<<grid, kThreads, smem, c->stream>>>(p, n_tiles);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_agg_columns_mode(fa_ctx *c, const SubmitParams &p, int grid)
+{
+    k_aggregate_columns<MODE><<<grid, kThreads, 0, c->stream>>>(p, c->cols);
+    return cudaGetLastError();
+}
+
+#define FA_DISPATCH_MODE(mode, CALL)                       \
+    switch (mode) {                                        \
+    case FA_KEY_FLOWS5M: e = CALL(FA_KEY_FLOWS5M); break;  \
+    case FA_KEY_ASPAIR: e = CALL(FA_KEY_ASPAIR); break;    \
+    case FA_KEY_SRCADDR: e = CALL(FA_KEY_SRCADDR); break;  \
+    case FA_KEY_DSTADDR: e = CALL(FA_KEY_DSTADDR); break;  \
+    case FA_KEY_5TUPLE: e = CALL(FA_KEY_5TUPLE); break;    \
+    case FA_KEY_SRCPORT: e = CALL(FA_KEY_SRCPORT); break;  \
+    default: e = CALL(FA_KEY_DSTPORT); break;              \
+    }
+
+// Launch decode(+aggregate) over records already in device memory.
+static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t len, const uint32_t *d_offsets,
+                        uint32_t n_records, uint32_t flags)
+{
+    if (n_records == 0) return FA_OK;
+    SubmitParams p{};
+    p.buf = d_buf;
+    p.base = base;
+    p.len = len;
+    p.offsets = d_offsets;
+    p.n_records = n_records;
+    p.framed = (flags & FA_FRAMED) ? 1u : 0u;
+    p.slots = c->d_slots;
+    p.slot_mask = (uint32_t)(c->capacity - 1);
+    p.scale = (c->cfg.flags & FA_CFG_SCALE_SAMPLING) ? 1u : 0u;
+    p.cms = c->d_cms;
+    p.cms_depth = c->cfg.cms_depth;
+    p.cms_wlog2 = c->cfg.cms_width_log2;
+    p.counters = c->d_counters;
+    const uint32_t n_tiles = (n_records + kTileRecords - 1) / kTileRecords;
+    const size_t smem = kTileBytes + kTilePad;
+    const int max_grid = c->num_sms * 5;  // 5 CTAs of 41 KB fit one SM's 227 KB
+    const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)max_grid);
+    cudaError_t e = cudaSuccess;
+    if (c->cfg.flags & FA_CFG_COLUMNS) {
+        if (n_records > c->cfg.max_batch_records) return FA_ERR_INVALID;
+        k_decode_columns<<<grid, kThreads, smem, c->stream>>>(p, n_tiles, c->cols);
+        e = cudaGetLastError();
+        c->cols_n = n_records;
+        if (e == cudaSuccess && !(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
+            const int g2 = (int)std::min<uint32_t>((n_records + kThreads - 1) / kThreads, (uint32_t)(c->num_sms * 8));
+#define CALL_AGG(M) launch_agg_columns_mode<M>(c, p, g2)
+            FA_DISPATCH_MODE(c->cfg.key_mode, CALL_AGG)
+#undef CALL_AGG
+        }
+    } else {
+#define CALL_FUSED(M) launch_fused_mode<M>(c, p, n_tiles, grid, smem)
+        FA_DISPATCH_MODE(c->cfg.key_mode, CALL_FUSED)
+#undef CALL_FUSED
+    }
+    FA_CUDA(c, e);
+    c->n_submits++;
+    c->n_records += n_records;
+    return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// framing on the GPU (offsets == NULL): see frame.cuh
+// ---------------------------------------------------------------------------------------------
+#include "frame.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// ingest
+// ---------------------------------------------------------------------------------------------
+
+static int ensure_staging(fa_ctx *c)
+{
+    if (c->d_stage[0]) return FA_OK;
+    for (int i = 0; i < 2; i++) {
+        FA_CUDA(c, cudaMalloc(&c->d_stage[i], c->cfg.max_batch_bytes + 256));
+        FA_CUDA(c, cudaMalloc(&c->d_stage_off[i], ((size_t)c->cfg.max_batch_records + 1) * 4));
+    }
+    return FA_OK;
+}
+
+extern "C" int fa_host_buffer(fa_ctx *c, int slot, uint8_t **buf, size_t *cap_bytes, uint32_t **offsets, size_t *cap_records)
+{
+    if (!c || slot < 0 || slot > 1) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (!c->h_slab[slot]) {
+        FA_CUDA(c, cudaHostAlloc(&c->h_slab[slot], c->cfg.max_batch_bytes, cudaHostAllocDefault));
+        FA_CUDA(c, cudaHostAlloc(&c->h_slab_off[slot], ((size_t)c->cfg.max_batch_records + 1) * 4, cudaHostAllocDefault));
+    } else {
+        FA_CUDA(c, cudaEventSynchronize(c->ev_slab[slot]));
+    }
+    if (buf) *buf = c->h_slab[slot];
+    if (cap_bytes) *cap_bytes = c->cfg.max_batch_bytes;
+    if (offsets) *offsets = c->h_slab_off[slot];
+    if (cap_records) *cap_records = c->cfg.max_batch_records;
+    return FA_OK;
+}
+
+extern "C" int fa_submit_device(fa_ctx *c, const uint8_t *d_buf, size_t len, const uint32_t *d_offsets, uint32_t n_records,
+                                uint32_t flags)
+{
+    if (!c || (!d_buf && len)) return FA_ERR_INVALID;
+    if (((uintptr_t)d_buf & 15u) || len > 0xFFFFFFF0ull) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (!d_offsets) {
+        if (!(flags & FA_FRAMED)) return FA_ERR_INVALID;
+        uint32_t n_found = 0;
+        int rc = frame_index_device(c, d_buf, len, &n_found);
+        if (rc) return rc;
+        d_offsets = c->d_frame_off;
+        n_records = n_found;
+    }
+    c->bytes_in += len;
+    return launch_batch(c, d_buf, 0, len, d_offsets, n_records, flags);
+}
+
+extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32_t *offsets, uint32_t n_records, uint32_t flags)
+{
+    if (!c || (!buf && len)) return FA_ERR_INVALID;
+    if (len > 0xFFFFFFF0ull) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    int rc = ensure_staging(c);
+    if (rc) return rc;
+    if (!offsets) {
+        // no boundaries from the host: stage the whole stream, index it on the GPU
+        if (!(flags & FA_FRAMED)) return FA_ERR_INVALID;
+        if (len > c->cfg.max_batch_bytes) return FA_ERR_INVALID;
+        const int i = c->next_stage;
+        c->next_stage ^= 1;
+        FA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[i], 0));
+        FA_CUDA(c, cudaMemcpyAsync(c->d_stage[i], buf, len, cudaMemcpyHostToDevice, c->copy_stream));
+        FA_CUDA(c, cudaEventRecord(c->ev_staged[i], c->copy_stream));
+        for (int s = 0; s < 2; s++)
+            if (buf >= c->h_slab[s] && c->h_slab[s] && buf < c->h_slab[s] + c->cfg.max_batch_bytes)
+                FA_CUDA(c, cudaEventRecord(c->ev_slab[s], c->copy_stream));
+        FA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_staged[i], 0));
+        uint32_t n_found = 0;
+        rc = frame_index_device(c, c->d_stage[i], len, &n_found);
+        if (rc) return rc;
+        c->bytes_in += len;
+        rc = launch_batch(c, c->d_stage[i], 0, len, c->d_frame_off, n_found, flags);
+        FA_CUDA(c, cudaEventRecord(c->ev_consumed[i], c->stream));
+        return rc;
+    }
+    if (n_records == 0) return FA_OK;
+    // cut into batches at record boundaries; copy of batch i+1 overlaps kernel of batch i
+    uint32_t r0 = 0;
+    while (r0 < n_records) {
+        const uint64_t a0 = offsets[r0] & ~15u;
+        const uint64_t lim = a0 + c->cfg.max_batch_bytes;
+        const uint32_t rmax = (uint32_t)std::min<uint64_t>((uint64_t)n_records, (uint64_t)r0 + c->cfg.max_batch_records);
+        // largest r1 in (r0, rmax] with offsets[r1] <= lim  (offsets assumed non-decreasing; the
+        // kernel re-validates every span)
+        const uint32_t *lo = offsets + r0 + 1, *hi = offsets + rmax + 1;
+        const uint32_t *it = std::upper_bound(lo, hi, (uint32_t)std::min<uint64_t>(lim, 0xFFFFFFFFull));
+        uint32_t r1 = (uint32_t)(it - offsets) - 1;
+        if (r1 <= r0) {
+            c->last_error = "a single record exceeds max_batch_bytes";
+            return FA_ERR_INVALID;
+        }
+        uint64_t b1 = offsets[r1];
+        if (b1 > len || b1 < a0) {  // corrupt offsets: clamp the copy, the kernel flags the records
+            b1 = std::min<uint64_t>(len, lim);
+            if (b1 < a0) b1 = a0;
+        }
+        const int i = c->next_stage;
+        c->next_stage ^= 1;
+        FA_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[i], 0));
+        if (b1 > a0) FA_CUDA(c, cudaMemcpyAsync(c->d_stage[i], buf + a0, b1 - a0, cudaMemcpyHostToDevice, c->copy_stream));
+        FA_CUDA(c, cudaMemcpyAsync(c->d_stage_off[i], offsets + r0, ((size_t)(r1 - r0) + 1) * 4, cudaMemcpyHostToDevice,
+                                   c->copy_stream));
+        FA_CUDA(c, cudaEventRecord(c->ev_staged[i], c->copy_stream));
+        FA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_staged[i], 0));
+        rc = launch_batch(c, c->d_stage[i], a0, b1 - a0, c->d_stage_off[i], r1 - r0, flags);
+        if (rc) return rc;
+        FA_CUDA(c, cudaEventRecord(c->ev_consumed[i], c->stream));
+        r0 = r1;
+    }
+    for (int s = 0; s < 2; s++)
+        if (c->h_slab[s] && buf >= c->h_slab[s] && buf < c->h_slab[s] + c->cfg.max_batch_bytes)
+            FA_CUDA(c, cudaEventRecord(c->ev_slab[s], c->copy_stream));
+    c->bytes_in += len;
+    return FA_OK;
+}
+
+extern "C" int fa_sync(fa_ctx *c)
+{
+    if (!c) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FA_OK;
+}
+
+static int read_counters(fa_ctx *c)
+{
+    FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FA_OK;
+}
+
+extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
+{
+    if (!c || !out) return FA_ERR_INVALID;
+    int rc = fa_sync(c);
+    if (rc) return rc;
+    rc = read_counters(c);
+    if (rc) return rc;
+    out->n_records = c->n_records;
+    out->n_bad = c->h_counters->n_bad;
+    out->n_nokey = c->h_counters->n_nokey;
+    out->n_dropped = c->h_counters->n_dropped;
+    out->n_groups = c->h_counters->n_groups;
+    out->n_submits = c->n_submits;
+    out->bytes_in = c->bytes_in;
+    return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// emit
+// ---------------------------------------------------------------------------------------------
+
+struct RowLess {
+    int kw;
+    bool operator()(const fa_row &a, const fa_row &b) const
+    {
+        for (int i = 0; i < kw; i++) {
+            if (a.key[i] != b.key[i]) return a.key[i] < b.key[i];
+        }
+        return false;
+    }
+};
+
+template <int KW>
+static cudaError_t launch_compact(fa_ctx *c, fa_row *d_rows, unsigned long long cap)
+{
+    const uint32_t n_slots = (uint32_t)std::min<uint64_t>(c->capacity, 0xFFFFFFFFull);
+    const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
+    k_compact_rows<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, d_rows, cap, c->d_counters);
+    return cudaGetLastError();
+}
+
+template <int KW>
+static cudaError_t launch_estimate(fa_ctx *c, const unsigned long long *cms, fa_hh *d_out, unsigned long long cap)
+{
+    const uint32_t n_slots = (uint32_t)std::min<uint64_t>(c->capacity, 0xFFFFFFFFull);
+    const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
+    k_estimate<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, cms, c->cfg.cms_depth, c->cfg.cms_width_log2, d_out, cap,
+                                                c->d_counters);
+    return cudaGetLastError();
+}
+
+#define FA_DISPATCH_KW(kw, CALL)     \
+    switch (kw) {                    \
+    case 1: e = CALL(1); break;      \
+    case 2: e = CALL(2); break;      \
+    case 4: e = CALL(4); break;      \
+    default: e = CALL(11); break;    \
+    }
+
+static int reset_table(fa_ctx *c)
+{
+    if (c->d_slots) FA_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->capacity * c->slot_bytes, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->n_groups, 0, 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->n_dropped, 0, 8, c->stream));
+    return FA_OK;
+}
+
+extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
+{
+    if (!c || !n || !c->d_slots) return FA_ERR_INVALID;
+    int rc = fa_sync(c);
+    if (rc) return rc;
+    rc = read_counters(c);
+    if (rc) return rc;
+    const uint64_t groups = c->h_counters->n_groups;
+    const uint64_t dropped = c->h_counters->n_dropped;
+    *n = (size_t)groups;
+    if (groups > cap || (groups && !rows)) return FA_ERR_CAPACITY;
+    if (groups) {
+        rc = ensure_scratch(c, groups * sizeof(fa_row));
+        if (rc) return rc;
+        FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+        cudaError_t e;
+#define CALL_COMPACT(K) launch_compact<K>(c, (fa_row *)c->d_scratch, groups)
+        FA_DISPATCH_KW(c->kw, CALL_COMPACT)
+#undef CALL_COMPACT
+        FA_CUDA(c, e);
+        FA_CUDA(c, cudaMemcpyAsync(rows, c->d_scratch, groups * sizeof(fa_row), cudaMemcpyDeviceToHost, c->stream));
+        FA_CUDA(c, cudaStreamSynchronize(c->stream));
+        // ORDER BY (Date, Timeslot, SrcAS, DstAS, ETypeMap.EType): create.sh:90
+        if (!(flags & FA_FLUSH_UNSORTED)) std::sort(rows, rows + groups, RowLess{c->kw});
+    }
+    if (!(flags & FA_FLUSH_KEEP)) {
+        rc = reset_table(c);
+        if (rc) return rc;
+    }
+    return dropped ? FA_ERR_TABLE_FULL : FA_OK;
+}
+
+extern "C" int fa_reset(fa_ctx *c)
+{
+    if (!c) return FA_ERR_INVALID;
+    int rc = fa_sync(c);
+    if (rc) return rc;
+    rc = reset_table(c);
+    if (rc) return rc;
+    if (c->d_cms) FA_CUDA(c, cudaMemsetAsync(c->d_cms, 0, c->cms_words * 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    c->n_records = c->n_submits = c->bytes_in = 0;
+    return fa_sync(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sketch / heavy hitters
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int fa_cms_read(fa_ctx *c, uint64_t *out, size_t cap_words)
+{
+    if (!c || !out || !c->d_cms) return FA_ERR_INVALID;
+    if (cap_words < c->cms_words) return FA_ERR_CAPACITY;
+    int rc = fa_sync(c);
+    if (rc) return rc;
+    FA_CUDA(c, cudaMemcpy(out, c->d_cms, c->cms_words * 8, cudaMemcpyDeviceToHost));
+    return FA_OK;
+}
+
+static int ensure_cms_global(fa_ctx *c)
+{
+    if (!c->d_cms) return FA_ERR_INVALID;
+    if (!c->d_cms_global) {
+        FA_CUDA(c, cudaMalloc(&c->d_cms_global, c->cms_words * 8));
+        FA_CUDA(c, cudaMemsetAsync(c->d_cms_global, 0, c->cms_words * 8, c->stream));
+    }
+    return FA_OK;
+}
+
+extern "C" int fa_cms_device(fa_ctx *c, int which, void **d_ptr, size_t *n_words)
+{
+    if (!c || !d_ptr || !c->d_cms) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (which == FA_CMS_GLOBAL) {
+        int rc = ensure_cms_global(c);
+        if (rc) return rc;
+        *d_ptr = c->d_cms_global;
+    } else {
+        *d_ptr = c->d_cms;
+    }
+    if (n_words) *n_words = c->cms_words;
+    return FA_OK;
+}
+
+struct HhLess {
+    int kw;
+    bool operator()(const fa_hh &a, const fa_hh &b) const
+    {
+        if (a.estimate != b.estimate) return a.estimate > b.estimate;
+        for (int i = 0; i < kw; i++) {
+            if (a.key[i] != b.key[i]) return a.key[i] < b.key[i];
+        }
+        return false;
+    }
+};
+
+extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t *n)
+{
+    if (!c || !n || !c->d_cms || !c->d_slots || (k && !out)) return FA_ERR_INVALID;
+    int rc = fa_sync(c);
+    if (rc) return rc;
+    rc = read_counters(c);
+    if (rc) return rc;
+    const uint64_t groups = c->h_counters->n_groups;
+    *n = 0;
+    if (!groups || !k) return FA_OK;
+    const unsigned long long *cms = c->d_cms;
+    if (which == FA_CMS_GLOBAL) {
+        rc = ensure_cms_global(c);
+        if (rc) return rc;
+        cms = c->d_cms_global;
+    }
+    rc = ensure_scratch(c, groups * sizeof(fa_hh));
+    if (rc) return rc;
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+    cudaError_t e;
+#define CALL_EST(K) launch_estimate<K>(c, cms, (fa_hh *)c->d_scratch, groups)
+    FA_DISPATCH_KW(c->kw, CALL_EST)
+#undef CALL_EST
+    FA_CUDA(c, e);
+    std::vector<fa_hh> all(groups);
+    FA_CUDA(c, cudaMemcpyAsync(all.data(), c->d_scratch, groups * sizeof(fa_hh), cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t kk = std::min<size_t>(k, groups);
+    std::partial_sort(all.begin(), all.begin() + kk, all.end(), HhLess{c->kw});
+    memcpy(out, all.data(), kk * sizeof(fa_hh));
+    *n = kk;
+    return FA_OK;
+}
+
+extern "C" int fa_topk_merge(const fa_hh *lists, size_t n_total, int key_words, size_t k, fa_hh *out, size_t *n)
+{
+    if (!n || (n_total && !lists) || key_words < 1 || key_words > FA_MAX_KEY_WORDS) return FA_ERR_INVALID;
+    std::vector<fa_hh> v(lists, lists + n_total);
+    HhLess less{key_words};
+    std::sort(v.begin(), v.end(), less);
+    // the same key may come from several contexts (same global estimate): keep one
+    size_t w = 0;
+    for (size_t i = 0; i < v.size(); i++) {
+        if (w && memcmp(v[w - 1].key, v[i].key, sizeof(uint32_t) * key_words) == 0 && v[w - 1].estimate == v[i].estimate) continue;
+        v[w++] = v[i];
+    }
+    const size_t kk = std::min(k, w);
+    if (kk && !out) return FA_ERR_INVALID;
+    memcpy(out, v.data(), kk * sizeof(fa_hh));
+    *n = kk;
+    return FA_OK;
+}
+
+// ---- NCCL (dlopen'ed so hosts that never ask for a box-wide top-K need no NCCL) ----
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::vector<int> devs;
+    std::vector<ncclComm_t> comms;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool nccl_load(std::string &err)
+{
+    if (g_nccl.lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        err = std::string("dlopen libnccl.so.2 failed: ") + dlerror();
+        return false;
+    }
+#define SYM(f, name)                                              \
+    *(void **)(&g_nccl.f) = dlsym(g_nccl.lib, name);              \
+    if (!g_nccl.f) {                                              \
+        err = std::string("missing NCCL symbol ") + name;         \
+        return false;                                             \
+    }
+    SYM(CommInitAll, "ncclCommInitAll")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return true;
+}
+}  // namespace
+
+extern "C" int fa_topk(fa_ctx *const *ctxs, int n_ctx, size_t k, fa_hh *out, size_t *n)
+{
+    if (!ctxs || n_ctx < 1 || !n) return FA_ERR_INVALID;
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i] || !ctxs[i]->d_cms || ctxs[i]->kw != ctxs[0]->kw || ctxs[i]->cms_words != ctxs[0]->cms_words) return FA_ERR_INVALID;
+    }
+    int which = FA_CMS_LOCAL;
+    if (n_ctx > 1) {
+        std::lock_guard<std::mutex> lk(g_nccl_mu);
+        fa_ctx *c0 = ctxs[0];
+        std::string err;
+        if (!nccl_load(err)) {
+            c0->last_error = err;
+            return FA_ERR_NCCL;
+        }
+        std::vector<int> devs(n_ctx);
+        for (int i = 0; i < n_ctx; i++) devs[i] = ctxs[i]->cfg.device;
+        if (g_nccl.devs != devs) {
+            for (ncclComm_t cm : g_nccl.comms) g_nccl.CommDestroy(cm);
+            g_nccl.comms.assign(n_ctx, nullptr);
+            int r = g_nccl.CommInitAll(g_nccl.comms.data(), n_ctx, devs.data());
+            if (r != 0) {
+                c0->last_error = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r);
+                g_nccl.comms.clear();
+                g_nccl.devs.clear();
+                return FA_ERR_NCCL;
+            }
+            g_nccl.devs = devs;
+        }
+        for (int i = 0; i < n_ctx; i++) {
+            int rc = fa_sync(ctxs[i]);
+            if (rc) return rc;
+            cudaSetDevice(ctxs[i]->cfg.device);
+            rc = ensure_cms_global(ctxs[i]);
+            if (rc) return rc;
+        }
+        // CMS is linear: the sum of the sketches is the sketch of the union of the partitions
+        g_nccl.GroupStart();
+        int r = 0;
+        for (int i = 0; i < n_ctx && r == 0; i++) {
+            cudaSetDevice(ctxs[i]->cfg.device);
+            r = g_nccl.AllReduce(ctxs[i]->d_cms, ctxs[i]->d_cms_global, ctxs[i]->cms_words, /*ncclUint64*/ 5, /*ncclSum*/ 0,
+                                 g_nccl.comms[i], ctxs[i]->stream);
+        }
+        int r2 = g_nccl.GroupEnd();
+        if (r != 0 || r2 != 0) {
+            c0->last_error = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r ? r : r2);
+            return FA_ERR_NCCL;
+        }
+        which = FA_CMS_GLOBAL;
+    }
+    std::vector<fa_hh> lists;
+    for (int i = 0; i < n_ctx; i++) {
+        std::vector<fa_hh> part(k);
+        size_t got = 0;
+        int rc = fa_topk_local(ctxs[i], which, k, part.data(), &got);
+        if (rc) return rc;
+        lists.insert(lists.end(), part.begin(), part.begin() + got);
+    }
+    return fa_topk_merge(lists.data(), lists.size(), ctxs[0]->kw, k, out, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel-1 columns
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int fa_columns(fa_ctx *c, fa_columns_view *v)
+{
+    if (!c || !v || !(c->cfg.flags & FA_CFG_COLUMNS)) return FA_ERR_INVALID;
+    const Columns &k = c->cols;
+    v->n_records = c->cols_n;
+    v->valid = k.valid;
+    v->time_received = (const uint64_t *)k.time_received;
+    v->time_flow_start = (const uint64_t *)k.time_flow_start;
+    v->sampling_rate = (const uint64_t *)k.sampling_rate;
+    v->bytes = (const uint64_t *)k.bytes;
+    v->packets = (const uint64_t *)k.packets;
+    v->type = k.type;
+    v->sequence_num = k.sequence_num;
+    v->src_as = k.src_as;
+    v->dst_as = k.dst_as;
+    v->etype = k.etype;
+    v->proto = k.proto;
+    v->src_port = k.src_port;
+    v->dst_port = k.dst_port;
+    v->src_addr = (const uint8_t *)k.src_addr;
+    v->dst_addr = (const uint8_t *)k.dst_addr;
+    v->sampler_addr = (const uint8_t *)k.sampler_addr;
+    v->src_addr_len = k.src_addr_len;
+    v->dst_addr_len = k.dst_addr_len;
+    v->sampler_addr_len = k.sampler_addr_len;
+    return FA_OK;
+}
+
+extern "C" int fa_columns_read(fa_ctx *c, const char *col, void *out, size_t cap_bytes)
+{
+    if (!c || !col || !out || !(c->cfg.flags & FA_CFG_COLUMNS)) return FA_ERR_INVALID;
+    const Columns &k = c->cols;
+    struct Ent { const char *name; const void *ptr; size_t elem; };
+    const Ent ents[] = {
+        {"valid", k.valid, 1}, {"time_received", k.time_received, 8}, {"time_flow_start", k.time_flow_start, 8},
+        {"sampling_rate", k.sampling_rate, 8}, {"bytes", k.bytes, 8}, {"packets", k.packets, 8}, {"type", k.type, 4},
+        {"sequence_num", k.sequence_num, 4}, {"src_as", k.src_as, 4}, {"dst_as", k.dst_as, 4}, {"etype", k.etype, 4},
+        {"proto", k.proto, 4}, {"src_port", k.src_port, 4}, {"dst_port", k.dst_port, 4}, {"src_addr", k.src_addr, 16},
+        {"dst_addr", k.dst_addr, 16}, {"sampler_addr", k.sampler_addr, 16}, {"src_addr_len", k.src_addr_len, 1},
+        {"dst_addr_len", k.dst_addr_len, 1}, {"sampler_addr_len", k.sampler_addr_len, 1}};
+    for (const Ent &e : ents) {
+        if (strcmp(e.name, col) == 0) {
+            const size_t bytes = e.elem * c->cols_n;
+            if (cap_bytes < bytes) return FA_ERR_CAPACITY;
+            int rc = fa_sync(c);
+            if (rc) return rc;
+            FA_CUDA(c, cudaMemcpy(out, e.ptr, bytes, cudaMemcpyDeviceToHost));
+            return FA_OK;
+        }
+    }
+    return FA_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------------------------------------
+// timing
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int fa_timer_start(fa_ctx *c)
+{
+    if (!c) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+    return FA_OK;
+}
+
+extern "C" int fa_timer_stop(fa_ctx *c, float *ms)
+{
+    if (!c || !ms) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    FA_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    FA_CUDA(c, cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return FA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mocker (mocker/mocker.go:57-102)
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int fa_mocker_host(const fa_mocker_config *cfg, uint64_t first, uint32_t n, uint8_t *buf, size_t cap, uint32_t *offsets,
+                              size_t *bytes)
+{
+    if (!cfg || !bytes) return FA_ERR_INVALID;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += fa_mocker_record_len(*cfg, first + i);
+    *bytes = (size_t)total;
+    if (total > 0xFFFFFFF0ull) return FA_ERR_INVALID;
+    if (total > cap || !buf || !offsets) return FA_ERR_CAPACITY;
+    uint8_t *p = buf;
+    for (uint32_t i = 0; i < n; i++) {
+        offsets[i] = (uint32_t)(p - buf);
+        p = fa_mocker_record_put(*cfg, first + i, p);
+    }
+    offsets[n] = (uint32_t)(p - buf);
+    return FA_OK;
+}
+
+__global__ void k_mocker_len(fa_mocker_config cfg, unsigned long long first, uint32_t n, uint32_t *offsets)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) offsets[0] = 0;
+    if (i < n) offsets[i + 1] = fa_mocker_record_len(cfg, first + i);
+}
+
+__global__ void k_mocker_put(fa_mocker_config cfg, unsigned long long first, uint32_t n, const uint32_t *offsets, uint8_t *buf)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fa_mocker_record_put(cfg, first + i, buf + offsets[i]);
+}
+
+extern "C" int fa_mocker_device(fa_ctx *c, const fa_mocker_config *cfg, uint64_t first, uint32_t n, uint8_t *d_buf, size_t cap,
+                                uint32_t *d_offsets, size_t *bytes)
+{
+    if (!c || !cfg || !d_buf || !d_offsets || !bytes) return FA_ERR_INVALID;
+    if (n > (1u << 25)) return FA_ERR_INVALID;  // keeps the u32 running sum below 2^32
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    *bytes = 0;
+    if (n == 0) return FA_OK;
+    const int grid = (int)((n + 255) / 256);
+    k_mocker_len<<<grid, 256, 0, c->stream>>>(*cfg, first, n, d_offsets);
+    FA_CUDA(c, cudaGetLastError());
+    size_t tmp = 0;
+    FA_CUDA(c, cub::DeviceScan::InclusiveSum(nullptr, tmp, d_offsets + 1, d_offsets + 1, (int)n, c->stream));
+    int rc = ensure_scratch(c, tmp);
+    if (rc) return rc;
+    FA_CUDA(c, cub::DeviceScan::InclusiveSum(c->d_scratch, tmp, d_offsets + 1, d_offsets + 1, (int)n, c->stream));
+    uint32_t total = 0;
+    FA_CUDA(c, cudaMemcpyAsync(&total, d_offsets + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    *bytes = total;
+    if (total > cap) return FA_ERR_CAPACITY;
+    k_mocker_put<<<grid, 256, 0, c->stream>>>(*cfg, first, n, d_offsets, d_buf);
+    FA_CUDA(c, cudaGetLastError());
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FA_OK;
+}

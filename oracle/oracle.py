@@ -1,0 +1,191 @@
+"""ctypes wrapper of the CPU ORACLE (oracle/flow_oracle.c).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package never
+imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FO_MAX_KEY_WORDS = 12
+KEY_MODES = {"flows5m": 0, "aspair": 1, "srcaddr": 2, "dstaddr": 3, "5tuple": 4, "srcport": 5, "dstport": 6}
+KEY_WORDS = [4, 2, 4, 4, 11, 1, 1]
+
+
+class FoFlow(C.Structure):
+    _fields_ = [
+        ("time_received", C.c_uint64), ("sampling_rate", C.c_uint64), ("time_flow_start", C.c_uint64),
+        ("bytes", C.c_uint64), ("packets", C.c_uint64),
+        ("type", C.c_uint32), ("sequence_num", C.c_uint32), ("src_as", C.c_uint32), ("dst_as", C.c_uint32),
+        ("etype", C.c_uint32), ("proto", C.c_uint32), ("src_port", C.c_uint32), ("dst_port", C.c_uint32),
+        ("src_addr_len", C.c_uint32), ("dst_addr_len", C.c_uint32), ("sampler_addr_len", C.c_uint32),
+        ("src_addr_off", C.c_uint32), ("dst_addr_off", C.c_uint32),
+        ("src_addr", C.c_uint8 * 16), ("dst_addr", C.c_uint8 * 16), ("sampler_addr", C.c_uint8 * 16),
+    ]
+
+
+ROW_DTYPE = np.dtype([("key", "<u4", (FO_MAX_KEY_WORDS,)), ("bytes", "<u8"), ("packets", "<u8"), ("count", "<u8")])
+HH_DTYPE = np.dtype([("key", "<u4", (FO_MAX_KEY_WORDS,)), ("estimate", "<u8")])
+
+
+class FoBatchResult(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_bad", C.c_uint64), ("n_nokey", C.c_uint64), ("seconds", C.c_double)]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.fo_decode.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(FoFlow)]
+        L.fo_decode.restype = C.c_int
+        L.fo_decode_record.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(FoFlow)]
+        L.fo_decode_record.restype = C.c_int
+        L.fo_frame_walk.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.fo_frame_walk.restype = C.c_long
+        L.fo_ip_string.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p]
+        L.fo_ip_string.restype = None
+        L.fo_key_words.argtypes = [C.c_int]
+        L.fo_make_key.argtypes = [C.c_int, C.POINTER(FoFlow), C.c_void_p]
+        L.fo_hash64.argtypes = [C.c_void_p, C.c_int]
+        L.fo_hash64.restype = C.c_uint64
+        L.fo_agg_new.argtypes = [C.c_int, C.c_int]
+        L.fo_agg_new.restype = C.c_void_p
+        L.fo_agg_free.argtypes = [C.c_void_p]
+        L.fo_agg_add.argtypes = [C.c_void_p, C.POINTER(FoFlow)]
+        L.fo_agg_add_row.argtypes = [C.c_void_p, C.c_void_p]
+        L.fo_agg_size.argtypes = [C.c_void_p]
+        L.fo_agg_size.restype = C.c_size_t
+        L.fo_agg_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.fo_agg_rows.restype = C.c_size_t
+        L.fo_cms_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64]
+        L.fo_cms_estimate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.fo_cms_estimate.restype = C.c_uint64
+        L.fo_topk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.fo_topk.restype = C.c_size_t
+        L.fo_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_int, C.POINTER(FoBatchResult)]
+        L.fo_run_batch.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+FLOW_FIELDS = ["time_received", "sampling_rate", "time_flow_start", "bytes", "packets", "type", "sequence_num",
+               "src_as", "dst_as", "etype", "proto", "src_port", "dst_port"]
+
+
+def decode(msg: bytes):
+    """proto.Unmarshal restatement -> (rc, dict).  rc 0 = ok, <0 = error class."""
+    f = FoFlow()
+    buf = (C.c_uint8 * max(len(msg), 1)).from_buffer_copy(msg or b"\0")
+    rc = lib().fo_decode(buf, len(msg), C.byref(f))
+    return rc, flow_dict(f)
+
+
+def flow_dict(f):
+    d = {k: int(getattr(f, k)) for k in FLOW_FIELDS}
+    d["src_addr"] = bytes(f.src_addr)
+    d["dst_addr"] = bytes(f.dst_addr)
+    d["sampler_addr"] = bytes(f.sampler_addr)
+    d["src_addr_len"] = int(f.src_addr_len)
+    d["dst_addr_len"] = int(f.dst_addr_len)
+    d["sampler_addr_len"] = int(f.sampler_addr_len)
+    return d
+
+
+def decode_columns(buf: np.ndarray, offsets: np.ndarray, framed: bool):
+    """Decode every record of a batch; returns dict of numpy columns (+ 'valid', 'rc')."""
+    L = lib()
+    n = len(offsets) - 1
+    cols = {k: np.zeros(n, dtype=np.uint64 if k in ("time_received", "sampling_rate", "time_flow_start", "bytes", "packets")
+                        else np.uint32) for k in FLOW_FIELDS}
+    for k in ("src_addr", "dst_addr", "sampler_addr"):
+        cols[k] = np.zeros((n, 16), dtype=np.uint8)
+        cols[k + "_len"] = np.zeros(n, dtype=np.uint32)
+    cols["valid"] = np.zeros(n, dtype=np.uint8)
+    cols["rc"] = np.zeros(n, dtype=np.int32)
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    ptr = buf.ctypes.data if buf.size else None
+    f = FoFlow()
+    for i in range(n):
+        rc = L.fo_decode_record(ptr, int(offsets[i]), int(offsets[i + 1]), int(framed), C.byref(f))
+        cols["rc"][i] = rc
+        if rc != 0:
+            continue
+        cols["valid"][i] = 1
+        for k in FLOW_FIELDS:
+            cols[k][i] = getattr(f, k)
+        for k in ("src_addr", "dst_addr", "sampler_addr"):
+            cols[k][i] = np.frombuffer(bytes(getattr(f, k)), dtype=np.uint8)
+            cols[k + "_len"][i] = getattr(f, k + "_len")
+    return cols
+
+
+def frame_walk(buf: np.ndarray):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = buf.size + 2
+    offs = np.zeros(cap, dtype=np.uint32)
+    n = lib().fo_frame_walk(buf.ctypes.data if buf.size else None, buf.size, offs.ctypes.data, cap)
+    return n, offs
+
+
+def ip_string(addr: bytes) -> str:
+    out = C.create_string_buffer(64 + 2 * len(addr))
+    b = (C.c_uint8 * max(len(addr), 1)).from_buffer_copy(addr or b"\0")
+    lib().fo_ip_string(b, len(addr), out)
+    return out.value.decode()
+
+
+def hash64(key_words) -> int:
+    k = np.ascontiguousarray(key_words, dtype=np.uint32)
+    return int(lib().fo_hash64(k.ctypes.data, len(k)))
+
+
+def run_batch(buf, offsets, framed=True, key_mode="flows5m", scale=False, cms=None, threads=1, aggregate=True):
+    """Decode + roll-up a whole batch.  Returns (rows ndarray ROW_DTYPE sorted, cms ndarray|None, result dict)."""
+    L = lib()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    n = len(offsets) - 1
+    mode = KEY_MODES[key_mode] if isinstance(key_mode, str) else int(key_mode)
+    agg = L.fo_agg_new(mode, int(scale)) if aggregate else None
+    cms_arr = None
+    depth = wlog2 = 0
+    if cms:
+        depth, wlog2 = cms
+        cms_arr = np.zeros(depth << wlog2, dtype=np.uint64)
+    res = FoBatchResult()
+    # without a table the C driver defaults the sketch key to SrcAddr; pass an agg to pick the mode
+    tmp_agg = agg
+    if agg is None and cms:
+        tmp_agg = L.fo_agg_new(mode, int(scale))
+    L.fo_run_batch(buf.ctypes.data if buf.size else None, offsets.ctypes.data, n, int(framed), tmp_agg,
+                   cms_arr.ctypes.data if cms_arr is not None else None, depth, wlog2, int(threads), C.byref(res))
+    rows = np.zeros(0, dtype=ROW_DTYPE)
+    if tmp_agg:
+        sz = L.fo_agg_size(tmp_agg)
+        rows = np.zeros(sz, dtype=ROW_DTYPE)
+        if sz:
+            L.fo_agg_rows(tmp_agg, rows.ctypes.data, sz)
+        L.fo_agg_free(tmp_agg)
+    return rows, cms_arr, {"n_records": res.n_records, "n_bad": res.n_bad, "n_nokey": res.n_nokey, "seconds": res.seconds}
+
+
+def topk(cms_arr, depth, wlog2, n_words, cand_rows, k):
+    out = np.zeros(k, dtype=HH_DTYPE)
+    cand_rows = np.ascontiguousarray(cand_rows)
+    n = lib().fo_topk(cms_arr.ctypes.data, depth, wlog2, n_words, cand_rows.ctypes.data if len(cand_rows) else None,
+                      len(cand_rows), k, out.ctypes.data)
+    return out[:n]
