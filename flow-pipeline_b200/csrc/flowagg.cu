@@ -426,8 +426,12 @@ extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32
         const uint32_t *it = std::upper_bound(lo, hi, (uint32_t)std::min<uint64_t>(lim, 0xFFFFFFFFull));
         uint32_t r1 = (uint32_t)(it - offsets) - 1;
         if (r1 <= r0) {
-            c->last_error = "a single record exceeds max_batch_bytes";
-            return FA_ERR_INVALID;
+            const uint64_t o0 = offsets[r0], o1 = offsets[r0 + 1];
+            if (o1 >= o0 && o1 <= len) {  // a sane span that genuinely does not fit
+                c->last_error = "a single record exceeds max_batch_bytes";
+                return FA_ERR_INVALID;
+            }
+            r1 = r0 + 1;  // corrupt span: ship it alone, the kernel flags it as a bad record
         }
         uint64_t b1 = offsets[r1];
         if (b1 > len || b1 < a0) {  // corrupt offsets: clamp the copy, the kernel flags the records

@@ -1,0 +1,353 @@
+"""GPU parity: the sm_100a kernels, driven through the C ABI (include/flowagg.h), against the
+CPU oracle and the golden vectors.  Bit-exact: everything on this path is integer/byte work."""
+import numpy as np
+import pytest
+
+from conftest import GOLD2ORACLE, concat_records, frame
+
+pytestmark = pytest.mark.gpu
+
+COLS = ["time_received", "sampling_rate", "time_flow_start", "bytes", "packets", "type", "sequence_num", "src_as", "dst_as",
+        "etype", "proto", "src_port", "dst_port", "src_addr", "dst_addr", "sampler_addr"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def gpu_columns(fp, blob, offs, framed, **kw):
+    with fp.FlowAgg(columns=True, aggregate=False, max_batch_records=max(len(offs) - 1, 1024), **kw) as a:
+        a.submit(blob, offs, framed=framed)
+        cols, st = a.columns()
+    n = len(offs) - 1
+    out = {}
+    for k, v in cols.items():
+        out[k] = v[: n * 16].reshape(n, 16) if k in ("src_addr", "dst_addr", "sampler_addr") else v[:n]
+    return out, st
+
+
+def assert_columns_equal(gpu, ora, n):
+    valid = ora["valid"].astype(bool)
+    assert np.array_equal(gpu["valid"].astype(bool), valid)
+    for k in COLS:
+        assert np.array_equal(gpu[k][valid], ora[k][valid].astype(gpu[k].dtype)), k
+        if k.endswith("_addr"):
+            assert np.array_equal(gpu[k + "_len"][valid], np.minimum(ora[k + "_len"][valid], 255)), k
+    # skipped records are zero rows (the inserter appends nothing for them, inserter.go:125-126)
+    for k in COLS:
+        assert not gpu[k][~valid].any(), k
+
+
+# ---------------------------------------------------------------- kernel 1: decode
+
+
+def test_edge_cases_decode(fp, oracle, edge_cases, torch_cuda):
+    msgs = [bytes.fromhex(c["hex"]) for c in edge_cases["cases"]]
+    blob, offs = concat_records(msgs)
+    gpu, st = gpu_columns(fp, blob, offs, framed=False)
+    want_ok = np.array([c["go_ok"] for c in edge_cases["cases"]])
+    bad = [c["name"] for c, g in zip(edge_cases["cases"], gpu["valid"]) if bool(g) != c["go_ok"]]
+    assert not bad, bad
+    assert st["n_bad"] == int((~want_ok).sum()) and st["n_records"] == len(msgs)
+    ora = oracle.decode_columns(blob, offs, framed=False)
+    assert_columns_equal(gpu, ora, len(msgs))
+    # and framed
+    fblob, foffs = concat_records(frame(msgs))
+    gpu2, _ = gpu_columns(fp, fblob, foffs, framed=True)
+    for k in gpu:
+        assert np.array_equal(gpu[k], gpu2[k]), k
+
+
+def test_fuzz_2k_decode_vs_golden_and_oracle(fp, oracle, fuzz_2k, torch_cuda):
+    g = fuzz_2k
+    gpu, st = gpu_columns(fp, g["blob"], g["offsets"], framed=False)
+    valid = g["valid"].astype(bool)
+    assert np.array_equal(gpu["valid"].astype(bool), valid)
+    for gk, ok in GOLD2ORACLE.items():
+        want = g[gk][valid]
+        assert np.array_equal(gpu[ok][valid], want.astype(gpu[ok].dtype)), gk
+    assert_columns_equal(gpu, oracle.decode_columns(g["blob"], g["offsets"], framed=False), len(valid))
+
+
+def test_mocker_10k_config0(fp, oracle, mocker_10k, torch_cuda):
+    """BASELINE.json configs[0]: 10k mocker messages, 1 partition, bare values (Postgres path)."""
+    g = mocker_10k
+    gpu, st = gpu_columns(fp, g["blob"], g["offsets"], framed=False)
+    assert st["n_bad"] == 0 and gpu["valid"].all()
+    for gk, ok in GOLD2ORACLE.items():
+        assert np.array_equal(gpu[ok], g[gk].astype(gpu[ok].dtype)), gk
+    with fp.FlowAgg("flows5m") as a:
+        a.submit(g["blob"], g["offsets"], framed=False)
+        rows = a.flush()
+        assert a.stats()["n_groups"] == 0  # flush resets the table
+    assert np.array_equal(rows["key"][:, :4], g["rollup_key"])           # pandas groupby
+    assert np.array_equal(np.stack([rows["bytes"], rows["packets"], rows["count"]], 1), g["rollup_val"])
+    want, _, _ = oracle.run_batch(g["blob"], g["offsets"], framed=False, key_mode="flows5m")
+    assert np.array_equal(rows, want)                                     # oracle, byte for byte
+    # the inserter's 14-column row for a few records (inserter.go:142-157)
+    for i in (0, 17, 9999):
+        assert oracle.ip_string(bytes(gpu["src_addr"][i][: gpu["src_addr_len"][i]])).startswith("2001:db8:0:1::")
+
+
+# ---------------------------------------------------------------- fused kernel 1 -> 2
+
+
+def mixed_batch(fp, fuzz_2k, n_mocker=60000, addr_mode=0, n_as=3, seed=5):
+    """mocker records with the fuzz set (bad records, SamplingRate != 1, odd addresses) spliced in"""
+    cfg = fp.FaMockerConfig.make(seed=seed, flows_per_second=100, n_src_as=n_as, n_dst_as=n_as, addr_mode=addr_mode, framed=True)
+    buf, offs = fp.mocker_host(cfg, 1000, n_mocker)
+    g = fuzz_2k
+    fmsgs = frame([bytes(g["blob"][g["offsets"][i]:g["offsets"][i + 1]]) for i in range(len(g["offsets"]) - 1)])
+    fb, fo = concat_records(fmsgs)
+    blob = np.concatenate([buf[: offs[n_mocker // 2]], fb, buf[offs[n_mocker // 2]:]])
+    o = np.concatenate([offs[: n_mocker // 2], fo[:-1] + offs[n_mocker // 2], offs[n_mocker // 2:] + fo[-1]]).astype(np.uint32)
+    return blob, o
+
+
+@pytest.mark.parametrize("mode", ["flows5m", "aspair", "srcaddr", "dstaddr", "5tuple", "srcport", "dstport"])
+@pytest.mark.parametrize("scale", [False, True])
+def test_fused_rollup_all_key_modes(fp, oracle, fuzz_2k, torch_cuda, mode, scale):
+    blob, offs = mixed_batch(fp, fuzz_2k, addr_mode=1 if mode == "srcaddr" else 0)
+    want, _, res = oracle.run_batch(blob, offs, framed=True, key_mode=mode, scale=scale)
+    with fp.FlowAgg(mode, scale_sampling=scale, table_capacity=1 << 18) as a:
+        a.submit(blob, offs, framed=True)
+        st = a.stats()
+        rows = a.flush()
+    assert st["n_bad"] == res["n_bad"] and st["n_nokey"] == res["n_nokey"] and st["n_groups"] == len(want)
+    assert np.array_equal(rows, want)
+    assert rows["count"].sum() == len(offs) - 1 - res["n_bad"] - res["n_nokey"]
+
+
+def test_unfused_k1_k2_equals_fused(fp, oracle, fuzz_2k, torch_cuda):
+    blob, offs = mixed_batch(fp, fuzz_2k)
+    for mode in ("flows5m", "5tuple"):
+        with fp.FlowAgg(mode, table_capacity=1 << 18) as a, fp.FlowAgg(mode, columns=True, table_capacity=1 << 18,
+                                                                         max_batch_records=len(offs)) as b:
+            a.submit(blob, offs)
+            b.submit(blob, offs)
+            assert np.array_equal(a.flush(), b.flush())
+
+
+def test_sketch_and_topk(fp, oracle, torch_cuda):
+    cfg = fp.FaMockerConfig.make(seed=9, flows_per_second=1000, addr_mode=1, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 300000)
+    d, wl = 4, 14
+    cand, cms, _ = oracle.run_batch(buf, offs, key_mode="srcaddr", cms=(d, wl))
+    with fp.FlowAgg("srcaddr", cms=True, cms_depth=d, cms_width_log2=wl, table_capacity=1 << 19) as a:
+        a.submit(buf, offs)
+        got = a.cms_read()
+        assert np.array_equal(got, cms)                       # counters bit-equal
+        top = a.topk_local(1000)
+        rows = a.flush(keep=True)
+        # linearity on the device: a second pass doubles every counter
+        a.submit(buf, offs)
+        assert np.array_equal(a.cms_read(), cms * 2)
+    assert np.array_equal(rows, cand)
+    want = oracle.topk(cms, d, wl, 4, cand, 1000)
+    assert np.array_equal(top["key"], want["key"]) and np.array_equal(top["estimate"], want["estimate"])
+    # recall of the sketch top-100 against the exact heavy hitters (viz-ch.json:233 semantic)
+    exact = cand[np.lexsort((cand["key"][:, 3], -cand["bytes"].astype(np.int64)))][:100]
+    hit = {bytes(k.tobytes()) for k in top["key"][:200]}
+    assert sum(bytes(k.tobytes()) in hit for k in exact["key"]) >= 90
+
+
+# ---------------------------------------------------------------- ingest paths and edge shapes
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 255, 256, 257, 1023, 5000])
+def test_ragged_sizes(fp, oracle, torch_cuda, n):
+    cfg = fp.FaMockerConfig.make(seed=2, flows_per_second=7, n_src_as=5, n_dst_as=4, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, n)
+    want, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
+    with fp.FlowAgg("flows5m") as a:
+        a.submit(buf, offs)
+        assert np.array_equal(a.flush(), want)
+
+
+def test_host_batching_and_slabs(fp, oracle, torch_cuda):
+    cfg = fp.FaMockerConfig.make(seed=4, flows_per_second=50, n_src_as=16, n_dst_as=16, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 100000)
+    want, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
+    # 64 KiB / 500-record staging forces ~170 pipelined batches
+    with fp.FlowAgg("flows5m", max_batch_bytes=64 << 10, max_batch_records=500) as a:
+        a.submit(buf, offs)
+        st = a.stats()
+        assert st["n_submits"] > 100 and st["n_records"] == 100000
+        assert np.array_equal(a.flush(), want)
+    # the pinned slabs a Go host would memcpy into, alternating, slab-relative offsets
+    with fp.FlowAgg("flows5m", max_batch_bytes=1 << 20, max_batch_records=8192) as a:
+        r = 0
+        slot = 0
+        while r < 100000:
+            hb, ho = a.host_buffer(slot)
+            r1 = min(r + 8000, 100000)
+            nb = int(offs[r1] - offs[r])
+            hb[:nb] = buf[offs[r]:offs[r1]]
+            ho[: r1 - r + 1] = offs[r:r1 + 1] - offs[r]
+            a.submit(hb, ho[: r1 - r + 1], nbytes=nb)
+            r = r1
+            slot ^= 1
+        assert np.array_equal(a.flush(), want)
+
+
+def test_device_submit_and_device_mocker(fp, oracle, torch_cuda):
+    torch = torch_cuda
+    n = 200000
+    cfg = fp.FaMockerConfig.make(seed=6, flows_per_second=500, n_src_as=256, n_dst_as=256, framed=True)
+    hbuf, hoffs = fp.mocker_host(cfg, 77, n)
+    want, _, _ = oracle.run_batch(hbuf, hoffs, key_mode="aspair")
+    with fp.FlowAgg("aspair", stream=torch.cuda.current_stream().cuda_stream) as a:
+        d_buf = torch.empty(n * 96, dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        nb = a.mocker_device(cfg, 77, n, d_buf, d_buf.numel(), d_off)
+        assert nb == len(hbuf)
+        assert np.array_equal(d_buf[:nb].cpu().numpy(), hbuf)             # same bytes on CPU and GPU
+        assert np.array_equal(d_off.cpu().numpy().view(np.uint32), hoffs)
+        a.submit_device(d_buf, d_off, n, nb)
+        assert np.array_equal(a.flush(), want)
+
+
+def test_tile_too_big_for_shared_memory_falls_back_to_global(fp, oracle, torch_cuda):
+    cfg = fp.FaMockerConfig.make(seed=8, flows_per_second=10, framed=False)
+    buf, offs = fp.mocker_host(cfg, 0, 3000)
+    msgs = [bytes(buf[offs[i]:offs[i + 1]]) for i in range(3000)]
+    big = b"\xc2\x3e" + b"\xe0\xd4\x03" + b"z" * 60000  # unknown field 1000, 60 000 bytes
+    for i in (5, 300, 301, 1500, 2999):
+        msgs[i] = big + msgs[i] + big
+    for framed in (False, True):
+        blob, o = concat_records(frame(msgs) if framed else msgs)
+        want, _, res = oracle.run_batch(blob, o, framed=framed, key_mode="5tuple")
+        assert res["n_bad"] == 0
+        with fp.FlowAgg("5tuple", table_capacity=1 << 14) as a:
+            a.submit(blob, o, framed=framed)
+            assert np.array_equal(a.flush(), want)
+
+
+def test_corrupt_offsets_are_bad_records_not_crashes(fp, oracle, torch_cuda):
+    cfg = fp.FaMockerConfig.make(seed=10, flows_per_second=10, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 2000)
+    bad = offs.copy()
+    bad[700] = bad[703]          # record 699 swallows three, 700..702 become empty/negative spans
+    bad[1200] = 0xFFFFFFF0       # far outside the buffer
+    bad[1500] = bad[1499] - 5    # decreasing
+    with fp.FlowAgg("flows5m") as a:
+        a.submit(buf, bad)
+        st = a.stats()
+        rows = a.flush()
+    assert 4 <= st["n_bad"] <= 12 and rows["count"].sum() == 2000 - st["n_bad"]
+
+
+def test_null_offsets_framing_on_gpu(fp, oracle, fuzz_2k, torch_cuda):
+    blob, offs = mixed_batch(fp, fuzz_2k, n_mocker=200000)
+    want, _, res = oracle.run_batch(blob, offs, framed=True, key_mode="flows5m")
+    with fp.FlowAgg("flows5m") as a:
+        a.submit(blob, None, framed=True)
+        st = a.stats()
+        assert st["n_records"] == len(offs) - 1 and st["n_bad"] == res["n_bad"]
+        assert np.array_equal(a.flush(), want)
+    # adversarial payloads: long zero runs and embedded bytes that look like record headers
+    rng = np.random.default_rng(3)
+    msgs = []
+    for i in range(20000):
+        k = int(rng.integers(0, 4))
+        pay = [bytes(int(rng.integers(0, 300))), b"\x50" * int(rng.integers(0, 200)), bytes(rng.integers(0, 256, int(rng.integers(0, 400)), dtype=np.uint8)),
+               b"\x02\x48\x05" * int(rng.integers(0, 90))][k]
+        n = len(pay)
+        ln = b""
+        while True:
+            b = n & 0x7F
+            n >>= 7
+            if n:
+                ln += bytes([b | 0x80])
+            else:
+                ln += bytes([b])
+                break
+        msgs.append(b"\x62" + ln + pay + b"\x48" + bytes([i % 100 + 1]) + b"\x70\x01\x78\x02")  # NextHop blob, Bytes, SrcAS, DstAS
+    fblob, foffs = concat_records(frame(msgs))
+    want, _, res = oracle.run_batch(fblob, foffs, framed=True, key_mode="aspair")
+    with fp.FlowAgg("aspair") as a:
+        a.submit(fblob, None, framed=True)
+        assert a.stats()["n_records"] == 20000
+        assert np.array_equal(a.flush(), want)
+        # a stream cut inside the last record: the tail is one bad record
+        a.submit(fblob[:-3], None, framed=True)
+        st = a.stats()
+        assert st["n_records"] == 40000 and st["n_bad"] == 1
+
+
+def test_table_full_is_reported_not_silent(fp, torch_cuda):
+    cfg = fp.FaMockerConfig.make(seed=12, flows_per_second=10, addr_mode=2, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 5000)
+    with fp.FlowAgg("5tuple", table_capacity=1024) as a:
+        a.submit(buf, offs)
+        st = a.stats()
+        assert st["n_groups"] == 1024 and st["n_dropped"] == 5000 - 1024
+        rows = a.flush(allow_full=True)
+        assert len(rows) == 1024 and rows["count"].sum() == 1024
+
+
+def test_box_topk_single_process_multi_gpu(fp, oracle, torch_cuda):
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    cfg = fp.FaMockerConfig.make(seed=13, flows_per_second=1000, addr_mode=1, framed=True)
+    parts = [fp.mocker_host(cfg, p * 50000, 50000) for p in range(2)]
+    ctxs = [fp.FlowAgg("srcaddr", device=p, cms=True, cms_width_log2=14, table_capacity=1 << 18) for p in range(2)]
+    for c, (b, o) in zip(ctxs, parts):
+        c.submit(b, o)
+    top = fp.FlowAgg.topk(ctxs, 100)
+    buf, offs = fp.mocker_host(cfg, 0, 100000)
+    cand, cms, _ = oracle.run_batch(buf, offs, key_mode="srcaddr", cms=(4, 14))
+    want = oracle.topk(cms, 4, 14, 4, cand, 100)
+    assert np.array_equal(top["key"], want["key"]) and np.array_equal(top["estimate"], want["estimate"])
+    top2 = fp.FlowAgg.topk(ctxs, 100)  # repeated query must not double count
+    assert np.array_equal(top2["estimate"], want["estimate"])
+    for c in ctxs:
+        c.close()
+
+
+# ---------------------------------------------------------------- BASELINE.json configs[1] at full size
+
+
+def test_config1_full_size_properties(fp, oracle, torch_cuda):
+    """100M mocker FlowMessages, (SrcAS,DstAS) group-by, 64k pairs: size-independent properties."""
+    torch = torch_cuda
+    n_total, slab = 100_000_000, 1 << 24
+    cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True)
+    d_buf = torch.empty(slab * 90, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(slab + 1, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    with fp.FlowAgg("aspair", stream=s) as a, fp.FlowAgg("aspair", stream=s) as first:
+        done = 0
+        first_rows = None
+        while done < n_total:
+            n = min(slab, n_total - done)
+            nb = a.mocker_device(cfg, done, n, d_buf, d_buf.numel(), d_off)
+            a.submit_device(d_buf, d_off, n, nb)
+            if done == 0:
+                # slab 0 again, in a second context fed two halves in reverse order (order/split invariance)
+                half = n // 2
+                offs = d_off.cpu().numpy().view(np.uint32)
+                first.submit_device(d_buf, d_off[half:], n - half, nb)
+                first.submit_device(d_buf, d_off, half, int(offs[half]))
+                first_rows = first.flush()
+                # oracle on the first 2M records of the slab
+                m = 2_000_000
+                hb = d_buf[: int(offs[m])].cpu().numpy()
+                want, _, _ = oracle.run_batch(hb, offs[: m + 1], key_mode="aspair", threads=8)
+                first.submit_device(d_buf, d_off, m, int(offs[m]))
+                assert np.array_equal(first.flush(), want)
+            a.sync()
+            done += n
+        st = a.stats()
+        slab0 = None
+        rows = a.flush()
+    assert st["n_records"] == n_total and st["n_bad"] == 0 and st["n_groups"] == 65536
+    assert rows["count"].sum() == n_total and len(rows) == 65536
+    assert rows["count"].min() > 1000 and rows["count"].max() < 2100       # uniform pairs: ~1526 each
+    assert first_rows["count"].sum() == slab and (rows["count"] >= first_rows["count"]).all()
+    # Bytes ~ U[0,1500), Packets ~ U[0,100): mocker.go:59-60
+    assert abs(rows["bytes"].sum() / n_total - 749.5) < 0.5 and abs(rows["packets"].sum() / n_total - 49.5) < 0.05

@@ -1,0 +1,106 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_symbol_of_the_header(fp):
+    hdr = open(os.path.join(ROOT, "include", "flowagg.h")).read()
+    declared = set(re.findall(r"^(?:int|void|const char \*)\s*\*?(fa_[a-z_0-9]+)\s*\(", hdr, re.M))
+    assert len(declared) >= 20
+    import ctypes as C
+
+    L = C.CDLL(fp.lib_path())
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libflowagg.so does not export {name}"
+    assert declared == set(__import__("flow_pipeline_b200").flowagg.exported_symbols()), "binding and header diverge"
+    L.fa_build_info.restype = C.c_char_p
+    assert b"sm_100a" in L.fa_build_info()
+
+
+def test_library_carries_sm100a_code_only(fp):
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", fp.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_gpu_means_loud_failure_not_fallback(fp):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fp.FlowAggError) as e:
+        fp.FlowAgg()
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "flow-pipeline_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                bad = re.search(r"(^\s*(from|import)\s+oracle\b)|(#include\s+\"[^\"]*oracle)|liboracle|fo_[a-z_]+\s*\(", src, re.M)
+                assert not bad, f"{f} links or calls the oracle: {bad.group(0)}"
+
+
+def test_mocker_host_is_bytewise_proto_marshal(fp, mocker_10k):
+    # golden blob = upb SerializeToString of the same fields (tests/golden/make_golden.py)
+    cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=20, framed=False)
+    buf, offs = fp.mocker_host(cfg, 0, 10000)
+    assert np.array_equal(buf, mocker_10k["blob"]) and np.array_equal(offs, mocker_10k["offsets"])
+
+
+def test_mocker_framed_and_modes_decode_with_oracle(fp, oracle):
+    for mode, n_as in ((0, 3), (1, 256), (2, 256)):
+        cfg = fp.FaMockerConfig.make(seed=7, flows_per_second=1000, n_src_as=n_as, n_dst_as=n_as, addr_mode=mode, framed=True)
+        buf, offs = fp.mocker_host(cfg, 12345, 4000)
+        cols = oracle.decode_columns(buf, offs, framed=True)
+        assert cols["valid"].all()
+        assert (cols["sampling_rate"] == 1).all() and (cols["etype"] == 0x86DD).all() and (cols["proto"] == 0).all()
+        assert cols["bytes"].max() < 1500 and cols["packets"].max() < 100            # mocker.go:59-60
+        assert cols["src_as"].min() >= 65000 and cols["src_as"].max() < 65000 + n_as  # mocker.go:61,79
+        assert np.array_equal(cols["sequence_num"], np.arange(12345, 12345 + 4000, dtype=np.uint32))
+        assert (cols["time_received"] == 1584912398 + np.arange(12345, 16345) // 1000).all()
+        assert (cols["src_addr"][:, :8] == np.frombuffer(bytes.fromhex("20010db800000001"), dtype=np.uint8)).all()
+        if mode == 2:  # unique 5-tuples
+            assert len({bytes(a) for a in cols["src_addr"]}) == 4000
+        # a different window of the same stream is the same bytes (counter-based generator)
+        buf2, offs2 = fp.mocker_host(cfg, 12345 + 1000, 100)
+        assert np.array_equal(buf2, buf[offs[1000]:offs[1100]])
+
+
+def test_topk_merge_is_pure_host_arithmetic(fp):
+    a = np.zeros(3, dtype=fp.HH_DTYPE)
+    b = np.zeros(3, dtype=fp.HH_DTYPE)
+    a["key"][:, 0] = [1, 2, 3]; a["estimate"] = [50, 40, 10]
+    b["key"][:, 0] = [2, 9, 8]; b["estimate"] = [40, 45, 45]
+    out = fp.FlowAgg.topk_merge([a, b], 1, 4)
+    assert list(out["estimate"]) == [50, 45, 45, 40]
+    assert list(out["key"][:, 0]) == [1, 8, 9, 2]  # ties by key ascending, duplicate key 2 kept once
+
+
+def test_sum_rows_by_key(fp):
+    import importlib
+
+    par = importlib.import_module("flow-pipeline_b200.parallel")
+    r = np.zeros(4, dtype=fp.ROW_DTYPE)
+    r["key"][:, 0] = [5, 1, 5, 1]; r["key"][:, 1] = [0, 2, 0, 3]
+    r["bytes"] = [1, 2, 3, 2**64 - 1]; r["packets"] = 1; r["count"] = 1
+    out = par.sum_rows_by_key(r, 2)
+    assert [tuple(k[:2]) for k in out["key"]] == [(1, 2), (1, 3), (5, 0)]
+    assert list(out["bytes"]) == [2, 2**64 - 1, 4] and list(out["count"]) == [1, 1, 2]
+
+
+def test_oracle_threads_agree(oracle, fp):
+    cfg = fp.FaMockerConfig.make(seed=3, flows_per_second=100, n_src_as=16, n_dst_as=16, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 50000)
+    r1, c1, _ = oracle.run_batch(buf, offs, key_mode="flows5m", cms=(4, 10), threads=1)
+    r8, c8, _ = oracle.run_batch(buf, offs, key_mode="flows5m", cms=(4, 10), threads=8)
+    assert np.array_equal(r1, r8) and np.array_equal(c1, c8)
