@@ -154,7 +154,7 @@ static int alloc_columns(fa_ctx *c)
 {
     const size_t n = c->cfg.max_batch_records;
     // one block: 5 u64, 8 u32, 3 x 16 B, 4 u8 columns
-    const size_t bytes = n * (5 * 8 + 8 * 4 + 3 * 16 + 4) + 1024;
+    const size_t bytes = n * (5 * 8 + 8 * 4 + 3 * 16 + 4) + 20 * 256 + 1024;
     FA_CUDA(c, cudaMalloc(&c->cols_block, bytes));
     uint8_t *p = (uint8_t *)c->cols_block;
     auto take = [&](size_t b) { uint8_t *r = p; p += (b + 255) & ~(size_t)255; return r; };
@@ -221,8 +221,8 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
         return FA_ERR_CUDA;
     }
     c->num_sms = prop.multiProcessorCount;
-    if (c->cfg.stream) {
-        c->stream = (cudaStream_t)c->cfg.stream;
+    if (c->cfg.stream || (c->cfg.flags & FA_CFG_CALLER_STREAM)) {
+        c->stream = (cudaStream_t)c->cfg.stream;  // NULL here = the legacy default stream
     } else {
         FA_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
@@ -425,18 +425,26 @@ extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32
         const uint32_t *lo = offsets + r0 + 1, *hi = offsets + rmax + 1;
         const uint32_t *it = std::upper_bound(lo, hi, (uint32_t)std::min<uint64_t>(lim, 0xFFFFFFFFull));
         uint32_t r1 = (uint32_t)(it - offsets) - 1;
-        if (r1 <= r0) {
-            const uint64_t o0 = offsets[r0], o1 = offsets[r0 + 1];
-            if (o1 >= o0 && o1 <= len) {  // a sane span that genuinely does not fit
-                c->last_error = "a single record exceeds max_batch_bytes";
-                return FA_ERR_INVALID;
+        if (r1 <= r0) r1 = r0 + 1;
+        // the batch must be a monotone run inside the buffer; stop at the first boundary that is not
+        bool lone_bad = offsets[r0] > len;
+        if (!lone_bad) {
+            uint32_t prev = offsets[r0], v = r0 + 1;
+            for (; v <= r1; v++) {
+                const uint32_t o = offsets[v];
+                if (o < prev || o > len) break;
+                prev = o;
             }
-            r1 = r0 + 1;  // corrupt span: ship it alone, the kernel flags it as a bad record
+            if (v <= r1) {
+                if (v == r0 + 1) lone_bad = true;  // record r0 itself has an insane span
+                else r1 = v - 1;
+            }
         }
-        uint64_t b1 = offsets[r1];
-        if (b1 > len || b1 < a0) {  // corrupt offsets: clamp the copy, the kernel flags the records
-            b1 = std::min<uint64_t>(len, lim);
-            if (b1 < a0) b1 = a0;
+        if (lone_bad) r1 = r0 + 1;
+        uint64_t b1 = lone_bad ? a0 : offsets[r1];
+        if (!lone_bad && b1 - a0 > c->cfg.max_batch_bytes) {
+            c->last_error = "a single record exceeds max_batch_bytes";
+            return FA_ERR_INVALID;
         }
         const int i = c->next_stage;
         c->next_stage ^= 1;
@@ -446,7 +454,8 @@ extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32
                                    c->copy_stream));
         FA_CUDA(c, cudaEventRecord(c->ev_staged[i], c->copy_stream));
         FA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_staged[i], 0));
-        rc = launch_batch(c, c->d_stage[i], a0, b1 - a0, c->d_stage_off[i], r1 - r0, flags);
+        // a lone record with an insane span is launched over an empty buffer: the kernel rejects and counts it
+        rc = launch_batch(c, c->d_stage[i], lone_bad ? 0 : a0, b1 - a0, c->d_stage_off[i], r1 - r0, flags);
         if (rc) return rc;
         FA_CUDA(c, cudaEventRecord(c->ev_consumed[i], c->stream));
         r0 = r1;

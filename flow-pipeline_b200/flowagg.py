@@ -24,6 +24,7 @@ FA_CFG_CMS = 0x1
 FA_CFG_SCALE_SAMPLING = 0x2
 FA_CFG_COLUMNS = 0x4
 FA_CFG_NO_AGGREGATE = 0x8
+FA_CFG_CALLER_STREAM = 0x10
 FA_FRAMED = 0x1
 FA_FLUSH_KEEP = 0x1
 FA_FLUSH_UNSORTED = 0x2
@@ -169,6 +170,8 @@ class FlowAgg:
         flags = (FA_CFG_CMS if cms else 0) | (FA_CFG_SCALE_SAMPLING if scale_sampling else 0) | (FA_CFG_COLUMNS if columns else 0)
         if not aggregate:
             flags |= FA_CFG_NO_AGGREGATE
+        if stream is not None:
+            flags |= FA_CFG_CALLER_STREAM  # also when the handle is 0: torch's default stream
         self.cfg = FaConfig(FA_ABI_VERSION, device, self.key_mode, flags, table_capacity, cms_depth, cms_width_log2,
                             max_batch_bytes, max_batch_records, 0, stream)
         self.cms_depth = cms_depth or 4

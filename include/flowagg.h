@@ -63,6 +63,8 @@ typedef enum fa_key_mode {
                                       the dashboards' weighting (viz-ch.json:74)          */
 #define FA_CFG_COLUMNS 0x4u      /* also materialise the decoded columns (kernel 1 output) */
 #define FA_CFG_NO_AGGREGATE 0x8u /* decode only (with FA_CFG_COLUMNS): no group table      */
+#define FA_CFG_CALLER_STREAM 0x10u /* run on fa_config.stream even when it is NULL (the legacy
+                                      default stream) instead of a private stream           */
 
 typedef struct fa_config {
     uint32_t abi_version;    /* FA_ABI_VERSION */
