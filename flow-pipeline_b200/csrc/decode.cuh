@@ -1,10 +1,10 @@
 // decode.cuh -- device-side proto3 decoder for flowprotob.FlowMessage.
 //
 // One thread decodes one record from a byte tile staged in shared memory (or,
-// for tiles that do not fit, straight from global memory).  The rules are those
-// of proto.Unmarshal as called at inserter/inserter.go:124 (golang/protobuf
-// v1.4.3 -> google.golang.org/protobuf, go.mod:7) for the field table of
-// pb-ext/flow.pb.go:58-143:
+// for records that do not fit the tile, straight from global memory).  The rules
+// are those of proto.Unmarshal as called at inserter/inserter.go:124
+// (golang/protobuf v1.4.3 -> google.golang.org/protobuf, go.mod:7) for the field
+// table of pb-ext/flow.pb.go:58-143:
 //   any field order; last value wins; bytes replaced; unknown numbers and known
 //   numbers with a foreign wire type skipped by wire type; groups skipped with
 //   matching end tags; uint32/enum keep the low 32 bits; varints <= 10 bytes with
@@ -15,9 +15,10 @@
 //
 // Hot path: an unaligned 64-bit window is assembled from three aligned 32-bit
 // shared-memory loads; a 1-2 byte tag and a <=5-byte varint (or a 1-byte length)
-// are decoded from that window without further loads or loops.  Everything else
-// (long varints, long tags, groups, UTF-8) takes a byte-wise slow path kept out
-// of line.
+// are decoded from that window branch-free; the value lands in the wanted
+// register through predicated selects (no switch, no local memory).  Long
+// varints, long tags, groups and UTF-8 take byte-wise slow paths kept out of
+// line; they return by value so nothing on the hot path has its address taken.
 #pragma once
 #include <stdint.h>
 
@@ -53,15 +54,13 @@ struct Flow {
 
 #define FA_MAX_GROUP_DEPTH 32
 
-// Byte source over aligned 32-bit words.  `words` may point to shared or global
-// memory (the compiler keeps the address space after inlining).  limit_word is
-// the last word index that may be touched (over-reads are clamped to it).
+// Byte source over aligned 32-bit words in GLOBAL memory; over-reads are clamped
+// to limit_word (the last word of the buffer).
 struct ByteSrc {
     const uint32_t *words;
     uint32_t limit_word;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return words[i < limit_word ? i : limit_word]; }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(words + (i < limit_word ? i : limit_word)); }
     __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return (word(pos >> 2) >> ((pos & 3u) * 8u)) & 0xffu; }
-    // bytes pos..pos+7 as little-endian (lo, hi)
     __device__ __forceinline__ void window(uint32_t pos, uint32_t &lo, uint32_t &hi) const
     {
         const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
@@ -71,47 +70,71 @@ struct ByteSrc {
     }
 };
 
-// byte source without clamping, for tiles resident in (padded) shared memory
+// Byte source over a tile resident in (padded) SHARED memory, addressed by its
+// 32-bit shared-window address so the loads are LDS, never generic.
 struct SmemSrc {
-    const uint32_t *words;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return words[i]; }
-    __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return (words[pos >> 2] >> ((pos & 3u) * 8u)) & 0xffu; }
+    uint32_t base;  // shared address of tile byte 0
+    __device__ __forceinline__ uint32_t word(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + i * 4u));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t byte(uint32_t pos) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + pos));
+        return v;
+    }
+    // bytes pos..pos+7 as little-endian (lo, hi)
     __device__ __forceinline__ void window(uint32_t pos, uint32_t &lo, uint32_t &hi) const
     {
-        const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
-        const uint32_t a = words[i], b = words[i + 1], c = words[i + 2];
-        lo = __funnelshift_r(a, b, sh);
-        hi = __funnelshift_r(b, c, sh);
+        const uint32_t a = base + (pos & ~3u), sh = (pos & 3u) * 8u;
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
+        lo = __funnelshift_r(w0, w1, sh);
+        hi = __funnelshift_r(w1, w2, sh);
     }
 };
 
-// ---- slow paths (out of line) -------------------------------------------------
+// ---- slow paths (out of line, everything by value) -----------------------------
 
-// protowire.ConsumeVarint, byte at a time.  Returns bytes consumed or 0 on error.
+struct VarintRes {
+    unsigned long long v;
+    uint32_t n;  // bytes consumed, 0 = error
+};
+
+// protowire.ConsumeVarint, byte at a time
 template <class Src>
-__device__ __noinline__ uint32_t varint_slow(const Src &s, uint32_t pos, uint32_t end, unsigned long long &v)
+__device__ __noinline__ VarintRes varint_slow(const Src s, uint32_t pos, uint32_t end)
 {
+    VarintRes r;
+    r.v = 0;
+    r.n = 0;
     unsigned long long x = 0;
     for (uint32_t i = 0; i < 10; i++) {
-        if (pos + i >= end) return 0;  // truncated
+        if (pos + i >= end) return r;  // truncated
         const unsigned long long y = s.byte(pos + i);
         if (i == 9) {
-            if (y >= 2) return 0;  // overflow
-            x |= y << 63;
-            v = x;
-            return 10;
+            if (y >= 2) return r;  // overflow
+            r.v = x | (y << 63);
+            r.n = 10;
+            return r;
         }
         x |= (y & 0x7f) << (7 * i);
         if (y < 0x80) {
-            v = x;
-            return i + 1;
+            r.v = x;
+            r.n = i + 1;
+            return r;
         }
     }
-    return 0;
+    return r;
 }
 
 template <class Src>
-__device__ __noinline__ bool utf8_valid(const Src &s, uint32_t pos, uint32_t n)
+__device__ __noinline__ bool utf8_valid(const Src s, uint32_t pos, uint32_t n)
 {
     uint32_t i = 0;
     while (i < n) {
@@ -145,36 +168,37 @@ __device__ __noinline__ bool utf8_valid(const Src &s, uint32_t pos, uint32_t n)
 // protowire.ConsumeFieldValue(StartGroupType): returns the position after the
 // matching end-group tag, or 0xFFFFFFFF on error.
 template <class Src>
-__device__ __noinline__ uint32_t skip_group(const Src &s, uint32_t pos, uint32_t end, uint32_t start_num)
+__device__ __noinline__ uint32_t skip_group(const Src s, uint32_t pos, uint32_t end, uint32_t start_num)
 {
     uint32_t stack[FA_MAX_GROUP_DEPTH];
     int depth = 0;
     stack[depth++] = start_num;
     while (depth > 0) {
-        unsigned long long tag, v;
-        uint32_t n = varint_slow(s, pos, end, tag);
-        if (!n) return 0xFFFFFFFFu;
-        pos += n;
-        const unsigned long long num = tag >> 3;
-        const uint32_t wt = (uint32_t)tag & 7u;
+        VarintRes t = varint_slow(s, pos, end);
+        if (!t.n) return 0xFFFFFFFFu;
+        pos += t.n;
+        const unsigned long long num = t.v >> 3;
+        const uint32_t wt = (uint32_t)t.v & 7u;
         if (num < 1 || num > 0x7fffffffull) return 0xFFFFFFFFu;
         switch (wt) {
-        case 0:
-            n = varint_slow(s, pos, end, v);
-            if (!n) return 0xFFFFFFFFu;
-            pos += n;
+        case 0: {
+            VarintRes v = varint_slow(s, pos, end);
+            if (!v.n) return 0xFFFFFFFFu;
+            pos += v.n;
             break;
+        }
         case 1:
             if (end - pos < 8) return 0xFFFFFFFFu;
             pos += 8;
             break;
-        case 2:
-            n = varint_slow(s, pos, end, v);
-            if (!n) return 0xFFFFFFFFu;
-            pos += n;
-            if (v > (unsigned long long)(end - pos)) return 0xFFFFFFFFu;
-            pos += (uint32_t)v;
+        case 2: {
+            VarintRes v = varint_slow(s, pos, end);
+            if (!v.n) return 0xFFFFFFFFu;
+            pos += v.n;
+            if (v.v > (unsigned long long)(end - pos)) return 0xFFFFFFFFu;
+            pos += (uint32_t)v.v;
             break;
+        }
         case 3:
             if (depth >= FA_MAX_GROUP_DEPTH) return 0xFFFFFFFFu;
             stack[depth++] = (uint32_t)num;
@@ -194,33 +218,31 @@ __device__ __noinline__ uint32_t skip_group(const Src &s, uint32_t pos, uint32_t
     return pos;
 }
 
-// ---- field stores ---------------------------------------------------------------
+// ---- field stores: predicated selects, no branches ----------------------------------
 
 template <uint32_t NEED>
-__device__ __forceinline__ void store_varint_field(Flow &f, uint32_t num, unsigned long long v)
+__device__ __forceinline__ void store_varint_field(Flow &f, const uint32_t num, const unsigned long long v)
 {
     // consumeUint64 / consumeUint32 / consumeEnum: last value wins, u32 = low 32 bits
-    switch (num) {
-    case 1: if (NEED & F_TYPE) f.type = (uint32_t)v; break;
-    case 2: if (NEED & F_TIME_RECEIVED) f.time_received = v; break;
-    case 3: if (NEED & F_SAMPLING_RATE) f.sampling_rate = v; break;
-    case 4: if (NEED & F_SEQUENCE_NUM) f.sequence_num = (uint32_t)v; break;
-    case 9: if (NEED & F_BYTES) f.bytes = v; break;
-    case 10: if (NEED & F_PACKETS) f.packets = v; break;
-    case 14: if (NEED & F_SRC_AS) f.src_as = (uint32_t)v; break;
-    case 15: if (NEED & F_DST_AS) f.dst_as = (uint32_t)v; break;
-    case 20: if (NEED & F_PROTO) f.proto = (uint32_t)v; break;
-    case 21: if (NEED & F_SRC_PORT) f.src_port = (uint32_t)v; break;
-    case 22: if (NEED & F_DST_PORT) f.dst_port = (uint32_t)v; break;
-    case 30: if (NEED & F_ETYPE) f.etype = (uint32_t)v; break;
-    case 38: if (NEED & F_TIME_FLOW_START) f.time_flow_start = v; break;
-    default: break;
-    }
+    const uint32_t v32 = (uint32_t)v;
+    if (NEED & F_TYPE) f.type = num == 1 ? v32 : f.type;
+    if (NEED & F_TIME_RECEIVED) f.time_received = num == 2 ? v : f.time_received;
+    if (NEED & F_SAMPLING_RATE) f.sampling_rate = num == 3 ? v : f.sampling_rate;
+    if (NEED & F_SEQUENCE_NUM) f.sequence_num = num == 4 ? v32 : f.sequence_num;
+    if (NEED & F_BYTES) f.bytes = num == 9 ? v : f.bytes;
+    if (NEED & F_PACKETS) f.packets = num == 10 ? v : f.packets;
+    if (NEED & F_SRC_AS) f.src_as = num == 14 ? v32 : f.src_as;
+    if (NEED & F_DST_AS) f.dst_as = num == 15 ? v32 : f.dst_as;
+    if (NEED & F_PROTO) f.proto = num == 20 ? v32 : f.proto;
+    if (NEED & F_SRC_PORT) f.src_port = num == 21 ? v32 : f.src_port;
+    if (NEED & F_DST_PORT) f.dst_port = num == 22 ? v32 : f.dst_port;
+    if (NEED & F_ETYPE) f.etype = num == 30 ? v32 : f.etype;
+    if (NEED & F_TIME_FLOW_START) f.time_flow_start = num == 38 ? v : f.time_flow_start;
 }
 
 // first min(len,16) payload bytes -> 4 big-endian words, zero right-padded
 template <class Src>
-__device__ __forceinline__ void load_addr(const Src &s, uint32_t pos, uint32_t len, uint32_t out[4])
+__device__ __forceinline__ void load_addr(const Src s, uint32_t pos, uint32_t len, uint32_t out[4])
 {
     const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
     uint32_t w[5];
@@ -237,38 +259,49 @@ __device__ __forceinline__ void load_addr(const Src &s, uint32_t pos, uint32_t l
     }
 }
 
+// varint whose bytes start at bit 0 of (xlo, xhi): <= 5 bytes decoded branch-free.
+// Returns the byte count (0 = longer than 5 bytes: take the slow path).
+__device__ __forceinline__ uint32_t varint5(uint32_t xlo, uint32_t xhi, unsigned long long &v)
+{
+    const uint32_t stop = ~xlo & 0x80808080u;              // terminator bytes among the first four
+    const uint32_t t = __ffs(stop);                        // 8,16,24,32, or 0 if none
+    const bool five = stop == 0u;
+    const uint32_t keep = five ? 0xFFFFFFFFu : (0xFFFFFFFFu >> ((32u - t) & 31u));
+    const uint32_t x = xlo & keep;
+    const uint32_t low28 = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
+    const uint32_t b4 = five ? (xhi & 0x7fu) : 0u;        // fifth byte: bits 28..34
+    v = ((unsigned long long)(b4 >> 4) << 32) | (unsigned long long)(low28 | (b4 << 28));
+    if (five && (xhi & 0x80u)) return 0u;                  // six bytes or more
+    return five ? 5u : (t >> 3);
+}
+
 // ---- the decoder -------------------------------------------------------------------
 
 // Decode the message occupying [pos,end) of the source.  Returns true when
 // proto.Unmarshal would return nil.  `f` must be zero-initialised (m.Reset()).
 template <uint32_t NEED, class Src>
-__device__ __forceinline__ bool decode_message(const Src &s, uint32_t pos, const uint32_t end, Flow &f)
+__device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const uint32_t end, Flow &f)
 {
     while (pos < end) {
         uint32_t lo, hi;
         s.window(pos, lo, hi);
-        // ---- tag ----
+        // ---- tag: 1 or 2 bytes branch-free ----
         uint32_t tag, tn;
-        if (!(lo & 0x80u)) {
-            tag = lo & 0x7fu;
-            tn = 1;
-        } else if (!(lo & 0x8000u)) {
-            tag = (lo & 0x7fu) | ((lo >> 1) & 0x3f80u);
-            tn = 2;
-        } else {
-            unsigned long long t64;
-            tn = varint_slow(s, pos, end, t64);
-            if (!tn) return false;
-            if ((t64 >> 3) > 0x1fffffffull) return false;
-            tag = (uint32_t)t64;
-            s.window(pos + tn, lo, hi);  // re-centre the window on the value
-            pos += tn;
+        if ((lo & 0x8080u) == 0x8080u) {  // three bytes or more: rare (field numbers >= 2048)
+            const VarintRes t = varint_slow(s, pos, end);
+            if (!t.n || (t.v >> 3) > 0x1fffffffull) return false;
+            tag = (uint32_t)t.v;
+            pos += t.n;
+            s.window(pos, lo, hi);  // re-centre the window on the value
             tn = 0;
+        } else {
+            const bool one = !(lo & 0x80u);
+            tag = one ? (lo & 0x7fu) : ((lo & 0x7fu) | ((lo >> 1) & 0x3f80u));
+            tn = one ? 1u : 2u;
         }
         const uint32_t num = tag >> 3, wt = tag & 7u;
         if (num == 0) return false;
         pos += tn;
-        if (pos > end) return false;  // tag ran past the end (tn==2 with one byte left)
         // value window: bytes pos.. (at least 6 valid)
         const uint32_t sh = tn * 8u;
         const uint32_t xlo = __funnelshift_r(lo, hi, sh);
@@ -276,58 +309,51 @@ __device__ __forceinline__ bool decode_message(const Src &s, uint32_t pos, const
         if (wt == 0) {
             // ---- varint ----
             unsigned long long v;
-            uint32_t vn;
-            const uint32_t stop_lo = ~xlo & 0x80808080u;
-            if (stop_lo) {
-                // 1..4 bytes
-                const uint32_t t = __ffs(stop_lo);  // 8,16,24,32
-                vn = t >> 3;
-                const uint32_t x = xlo & (0xFFFFFFFFu >> (32u - t));
-                v = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
-            } else if (!(xhi & 0x80u)) {
-                // 5 bytes (every Unix timestamp since 1978)
-                vn = 5;
-                const uint32_t x = xlo;
-                const uint32_t low28 = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
-                v = (unsigned long long)low28 | ((unsigned long long)(xhi & 0x7fu) << 28);
-            } else {
-                vn = varint_slow(s, pos, end, v);
-                if (!vn) return false;
+            uint32_t vn = varint5(xlo, xhi, v);
+            if (vn == 0) {
+                const VarintRes r = varint_slow(s, pos, end);
+                if (!r.n) return false;
+                v = r.v;
+                vn = r.n;
             }
             pos += vn;
-            if (pos > end) return false;
+            if (pos > end) return false;  // tag or value ran past the end of the record
             store_varint_field<NEED>(f, num, v);
         } else if (wt == 2) {
             // ---- length-delimited ----
-            unsigned long long ln;
-            uint32_t vn;
+            uint32_t n, vn;
             if (!(xlo & 0x80u)) {
-                ln = xlo & 0x7fu;
+                n = xlo & 0x7fu;
                 vn = 1;
             } else {
-                vn = varint_slow(s, pos, end, ln);
-                if (!vn) return false;
+                const VarintRes r = varint_slow(s, pos, end);
+                if (!r.n || r.v > 0xFFFFFFFFull) return false;
+                n = (uint32_t)r.v;
+                vn = r.n;
             }
             pos += vn;
-            if (pos > end || ln > (unsigned long long)(end - pos)) return false;
-            const uint32_t n = (uint32_t)ln;
-            if (num == 6) {
-                if (NEED & F_SRC_ADDR) { load_addr(s, pos, n, f.src); f.src_len = n; }
-            } else if (num == 7) {
-                if (NEED & F_DST_ADDR) { load_addr(s, pos, n, f.dst); f.dst_len = n; }
-            } else if (num == 11) {
-                if (NEED & F_SAMPLER_ADDR) { load_addr(s, pos, n, f.sampler); f.sampler_len = n; }
+            if (pos > end || n > end - pos) return false;
+            if ((NEED & F_SRC_ADDR) && num == 6) {
+                load_addr(s, pos, n, f.src);
+                f.src_len = n;
+            } else if ((NEED & F_DST_ADDR) && num == 7) {
+                load_addr(s, pos, n, f.dst);
+                f.dst_len = n;
+            } else if ((NEED & F_SAMPLER_ADDR) && num == 11) {
+                load_addr(s, pos, n, f.sampler);
+                f.sampler_len = n;
             } else if (num == 100 || num == 101) {
                 if (!utf8_valid(s, pos, n)) return false;
             }
             pos += n;
         } else if (wt == 5) {
-            if (end - pos < 4) return false;
+            if (pos > end || end - pos < 4) return false;
             pos += 4;
         } else if (wt == 1) {
-            if (end - pos < 8) return false;
+            if (pos > end || end - pos < 8) return false;
             pos += 8;
         } else if (wt == 3) {
+            if (pos > end) return false;
             pos = skip_group(s, pos, end, num);
             if (pos == 0xFFFFFFFFu) return false;
         } else {
@@ -340,7 +366,7 @@ __device__ __forceinline__ bool decode_message(const Src &s, uint32_t pos, const
 // Decode the record occupying [pos,end): bare message, or varint(len) || message
 // whose length must fill the span exactly.
 template <uint32_t NEED, class Src>
-__device__ __forceinline__ bool decode_record(const Src &s, uint32_t pos, uint32_t end, bool framed, Flow &f)
+__device__ __forceinline__ bool decode_record(const Src s, uint32_t pos, uint32_t end, bool framed, Flow &f)
 {
     if (framed) {
         if (pos >= end) return false;
@@ -348,15 +374,15 @@ __device__ __forceinline__ bool decode_record(const Src &s, uint32_t pos, uint32
         s.window(pos, lo, hi);
         unsigned long long mlen;
         uint32_t n;
-        if (!(lo & 0x80u)) {
-            mlen = lo & 0x7fu;
-            n = 1;
-        } else if (!(lo & 0x8000u)) {
-            mlen = (lo & 0x7fu) | ((lo >> 1) & 0x3f80u);
-            n = 2;
+        if ((lo & 0x8080u) == 0x8080u) {
+            const VarintRes r = varint_slow(s, pos, end);
+            if (!r.n) return false;
+            mlen = r.v;
+            n = r.n;
         } else {
-            n = varint_slow(s, pos, end, mlen);
-            if (!n) return false;
+            const bool one = !(lo & 0x80u);
+            mlen = one ? (lo & 0x7fu) : ((lo & 0x7fu) | ((lo >> 1) & 0x3f80u));
+            n = one ? 1u : 2u;
         }
         if (pos + n > end || mlen != (unsigned long long)(end - pos - n)) return false;
         pos += n;

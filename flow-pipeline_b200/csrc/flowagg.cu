@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <mutex>
 #include <new>
@@ -68,6 +69,8 @@ struct fa_ctx {
     // flush / top-K scratch
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *h_bounce = nullptr;  // pinned landing area for flushed rows
+    size_t bounce_bytes = 0;
 
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
@@ -88,7 +91,7 @@ struct fa_ctx {
 
 static const int k_key_words[FA_KEY_MODES] = {4, 2, 4, 4, 11, 1, 1};
 
-static uint32_t slot_bytes_for(int kw) { return ((4u + 4u * (uint32_t)kw + 7u) & ~7u) + 24u; }
+static uint32_t slot_bytes_for(int kw) { return kw <= 2 ? 32u : (kw == 4 ? 48u : 72u); }
 
 extern "C" const char *fa_strerror(int s)
 {
@@ -120,6 +123,31 @@ static int ensure_scratch(fa_ctx *c, size_t bytes)
     return FA_OK;
 }
 
+template <int KW>
+static cudaError_t launch_table_init(fa_ctx *c)
+{
+    const unsigned long long n_slots = c->capacity + 1;
+    const unsigned long long words = n_slots * (SlotLayout<KW>::BYTES / 8);
+    const int grid = (int)std::min<unsigned long long>((words + 255) / 256, (unsigned long long)c->num_sms * 32);
+    k_table_init<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots);
+    return cudaGetLastError();
+}
+
+// empty table: all-ones keys (CAS layouts) / state 0 (wide keys), zero sums
+static int table_init(fa_ctx *c)
+{
+    if (!c->d_slots) return FA_OK;
+    cudaError_t e;
+    switch (c->kw) {
+    case 1: e = launch_table_init<1>(c); break;
+    case 2: e = launch_table_init<2>(c); break;
+    case 4: e = launch_table_init<4>(c); break;
+    default: e = launch_table_init<11>(c); break;
+    }
+    FA_CUDA(c, e);
+    return FA_OK;
+}
+
 extern "C" void fa_destroy(fa_ctx *c)
 {
     if (!c) return;
@@ -143,6 +171,7 @@ extern "C" void fa_destroy(fa_ctx *c)
     cudaFree(c->d_frame_off);
     cudaFree(c->cols_block);
     cudaFree(c->d_scratch);
+    cudaFreeHost(c->h_bounce);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -239,8 +268,9 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
     FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
-        FA_CUDA(c, cudaMalloc(&c->d_slots, c->capacity * c->slot_bytes));
-        FA_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->capacity * c->slot_bytes, c->stream));
+        FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
+        int rc = table_init(c);
+        if (rc) return rc;
     }
     if (c->cfg.flags & FA_CFG_CMS) {
         c->cms_words = (size_t)c->cfg.cms_depth << c->cfg.cms_width_log2;
@@ -259,12 +289,24 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 // kernel launch
 // ---------------------------------------------------------------------------------------------
 
-template <int MODE>
-static cudaError_t launch_fused_mode(fa_ctx *c, const SubmitParams &p, uint32_t n_tiles, int grid, size_t smem)
+template <class Consumer>
+static cudaError_t launch_tile(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
-    if (c->weighted) k_decode_aggregate<MODE, true><<<grid, kThreads, smem, c->stream>>>(p, n_tiles);
-    else k_decode_aggregate<MODE, false><<<grid, kThreads, smem, c->stream>>>(p, n_tiles);
+    const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;
+    static thread_local size_t configured = 0;  // per kernel instantiation and host thread
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
+        if (e != cudaSuccess) return e;
+        configured = kTileBytesMax + kTilePad + 16;
+    }
+    k_tile<Consumer><<<n_tiles, kThreads, smem, c->stream>>>(tp);
     return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_fused_mode(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
+{
+    return c->weighted ? launch_tile<AggConsumer<MODE, true>>(c, tp, n_tiles) : launch_tile<AggConsumer<MODE, false>>(c, tp, n_tiles);
 }
 
 template <int MODE>
@@ -290,7 +332,8 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
                         uint32_t n_records, uint32_t flags)
 {
     if (n_records == 0) return FA_OK;
-    SubmitParams p{};
+    TileParams tp{};
+    SubmitParams &p = tp.p;
     p.buf = d_buf;
     p.base = base;
     p.len = len;
@@ -304,15 +347,23 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.cms_depth = c->cfg.cms_depth;
     p.cms_wlog2 = c->cfg.cms_width_log2;
     p.counters = c->d_counters;
-    const uint32_t n_tiles = (n_records + kTileRecords - 1) / kTileRecords;
-    const size_t smem = kTileBytes + kTilePad;
-    const int max_grid = c->num_sms * 5;  // 5 CTAs of 41 KB fit one SM's 227 KB
-    const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)max_grid);
+    // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
+    // the shared-memory budget, fewer for fat records
+    const double avg = (double)len / (double)n_records;
+    uint32_t tr = kThreads;
+    while (tr > 32 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 32;
+    uint32_t tb = (uint32_t)((double)tr * avg * 1.06 + 512.0);
+    tb = (tb + 1023u) & ~1023u;
+    if (tb > (uint32_t)kTileBytesMax) tb = kTileBytesMax;
+    if (tb < 4096u) tb = 4096u;
+    p.tile_records = tr;
+    p.tile_bytes = tb;
+    tp.c = c->cols;
+    const uint32_t n_tiles = (n_records + tr - 1) / tr;
     cudaError_t e = cudaSuccess;
     if (c->cfg.flags & FA_CFG_COLUMNS) {
         if (n_records > c->cfg.max_batch_records) return FA_ERR_INVALID;
-        k_decode_columns<<<grid, kThreads, smem, c->stream>>>(p, n_tiles, c->cols);
-        e = cudaGetLastError();
+        e = launch_tile<ColConsumer>(c, tp, n_tiles);
         c->cols_n = n_records;
         if (e == cudaSuccess && !(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
             const int g2 = (int)std::min<uint32_t>((n_records + kThreads - 1) / kThreads, (uint32_t)(c->num_sms * 8));
@@ -321,7 +372,7 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
 #undef CALL_AGG
         }
     } else {
-#define CALL_FUSED(M) launch_fused_mode<M>(c, p, n_tiles, grid, smem)
+#define CALL_FUSED(M) launch_fused_mode<M>(c, tp, n_tiles)
         FA_DISPATCH_MODE(c->cfg.key_mode, CALL_FUSED)
 #undef CALL_FUSED
     }
@@ -504,21 +555,10 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
 // emit
 // ---------------------------------------------------------------------------------------------
 
-struct RowLess {
-    int kw;
-    bool operator()(const fa_row &a, const fa_row &b) const
-    {
-        for (int i = 0; i < kw; i++) {
-            if (a.key[i] != b.key[i]) return a.key[i] < b.key[i];
-        }
-        return false;
-    }
-};
-
 template <int KW>
 static cudaError_t launch_compact(fa_ctx *c, fa_row *d_rows, unsigned long long cap)
 {
-    const uint32_t n_slots = (uint32_t)std::min<uint64_t>(c->capacity, 0xFFFFFFFFull);
+    const unsigned long long n_slots = c->capacity + 1;  // + the side slot
     const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
     k_compact_rows<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, d_rows, cap, c->d_counters);
     return cudaGetLastError();
@@ -527,7 +567,7 @@ static cudaError_t launch_compact(fa_ctx *c, fa_row *d_rows, unsigned long long 
 template <int KW>
 static cudaError_t launch_estimate(fa_ctx *c, const unsigned long long *cms, fa_hh *d_out, unsigned long long cap)
 {
-    const uint32_t n_slots = (uint32_t)std::min<uint64_t>(c->capacity, 0xFFFFFFFFull);
+    const unsigned long long n_slots = c->capacity + 1;
     const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
     k_estimate<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, cms, c->cfg.cms_depth, c->cfg.cms_width_log2, d_out, cap,
                                                 c->d_counters);
@@ -544,9 +584,67 @@ static cudaError_t launch_estimate(fa_ctx *c, const unsigned long long *cms, fa_
 
 static int reset_table(fa_ctx *c)
 {
-    if (c->d_slots) FA_CUDA(c, cudaMemsetAsync(c->d_slots, 0, c->capacity * c->slot_bytes, c->stream));
+    int rc = table_init(c);
+    if (rc) return rc;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->n_groups, 0, 8, c->stream));
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->n_dropped, 0, 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->side_state, 0, 4, c->stream));
+    return FA_OK;
+}
+
+// ---- ORDER BY on the device: stable LSD radix sort (cub) over the key words, last word first ----
+__global__ void k_iota(uint32_t *perm, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = i;
+}
+__global__ void k_sort_key(const fa_row *rows, const uint32_t *perm, uint32_t n, int word, uint32_t *keys)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = rows[perm[i]].key[word];
+}
+__global__ void k_gather_rows(const fa_row *in, const uint32_t *perm, uint32_t n, fa_row *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+
+// rows (unsorted, device) -> sorted (device); returns the pointer holding the sorted rows
+static int sort_rows_device(fa_ctx *c, size_t groups, fa_row **sorted)
+{
+    const uint32_t n = (uint32_t)groups;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (int)n, 0, 32, c->stream);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t rows_b = al(groups * sizeof(fa_row)), u32_b = al(groups * 4);
+    const size_t need = 2 * rows_b + 4 * u32_b + al(cub_bytes);
+    // the unsorted rows already sit at the start of the scratch block: grow it without losing them
+    if (need > c->scratch_bytes) {
+        void *bigger = nullptr;
+        FA_CUDA(c, cudaMalloc(&bigger, need));
+        FA_CUDA(c, cudaMemcpyAsync(bigger, c->d_scratch, groups * sizeof(fa_row), cudaMemcpyDeviceToDevice, c->stream));
+        FA_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_scratch);
+        c->d_scratch = bigger;
+        c->scratch_bytes = need;
+    }
+    uint8_t *base = (uint8_t *)c->d_scratch;
+    fa_row *rows_in = (fa_row *)base;
+    fa_row *rows_out = (fa_row *)(base + rows_b);
+    uint32_t *keys_a = (uint32_t *)(base + 2 * rows_b), *keys_b = (uint32_t *)(base + 2 * rows_b + u32_b);
+    uint32_t *perm_a = (uint32_t *)(base + 2 * rows_b + 2 * u32_b), *perm_b = (uint32_t *)(base + 2 * rows_b + 3 * u32_b);
+    void *cub_tmp = base + 2 * rows_b + 4 * u32_b;
+    const int g = (int)((n + 255) / 256);
+    k_iota<<<g, 256, 0, c->stream>>>(perm_a, n);
+    for (int w = c->kw - 1; w >= 0; w--) {
+        k_sort_key<<<g, 256, 0, c->stream>>>(rows_in, perm_a, n, w, keys_a);
+        FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, perm_a, perm_b, (int)n, 0, 32, c->stream));
+        std::swap(perm_a, perm_b);
+    }
+    k_gather_rows<<<g, 256, 0, c->stream>>>(rows_in, perm_a, n, rows_out);
+    FA_CUDA(c, cudaGetLastError());
+    *sorted = rows_out;
     return FA_OK;
 }
 
@@ -561,6 +659,7 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
     const uint64_t dropped = c->h_counters->n_dropped;
     *n = (size_t)groups;
     if (groups > cap || (groups && !rows)) return FA_ERR_CAPACITY;
+    if (groups >= (1ull << 31)) return FA_ERR_INVALID;
     if (groups) {
         rc = ensure_scratch(c, groups * sizeof(fa_row));
         if (rc) return rc;
@@ -570,10 +669,33 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
         FA_DISPATCH_KW(c->kw, CALL_COMPACT)
 #undef CALL_COMPACT
         FA_CUDA(c, e);
-        FA_CUDA(c, cudaMemcpyAsync(rows, c->d_scratch, groups * sizeof(fa_row), cudaMemcpyDeviceToHost, c->stream));
-        FA_CUDA(c, cudaStreamSynchronize(c->stream));
+        fa_row *src = (fa_row *)c->d_scratch;
         // ORDER BY (Date, Timeslot, SrcAS, DstAS, ETypeMap.EType): create.sh:90
-        if (!(flags & FA_FLUSH_UNSORTED)) std::sort(rows, rows + groups, RowLess{c->kw});
+        if (!(flags & FA_FLUSH_UNSORTED)) {
+            rc = sort_rows_device(c, groups, &src);
+            if (rc) return rc;
+        }
+        const size_t bytes = groups * sizeof(fa_row);
+        if (bytes <= (256u << 20)) {  // land in pinned memory, then one host memcpy into the caller's array
+            if (bytes > c->bounce_bytes) {
+                if (c->h_bounce) cudaFreeHost(c->h_bounce);
+                c->h_bounce = nullptr;
+                c->bounce_bytes = 0;
+                const size_t want = std::max<size_t>(bytes * 2, 1u << 20);
+                FA_CUDA(c, cudaHostAlloc(&c->h_bounce, want, cudaHostAllocDefault));
+                c->bounce_bytes = want;
+            }
+            FA_CUDA(c, cudaMemcpyAsync(c->h_bounce, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+            if (!(flags & FA_FLUSH_KEEP)) {
+                rc = reset_table(c);  // overlaps the copy on the same stream order
+                if (rc) return rc;
+            }
+            FA_CUDA(c, cudaStreamSynchronize(c->stream));
+            memcpy(rows, c->h_bounce, bytes);
+            return dropped ? FA_ERR_TABLE_FULL : FA_OK;
+        }
+        FA_CUDA(c, cudaMemcpyAsync(rows, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        FA_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     if (!(flags & FA_FLUSH_KEEP)) {
         rc = reset_table(c);

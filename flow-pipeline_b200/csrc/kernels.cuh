@@ -1,13 +1,19 @@
 // kernels.cuh -- sm_100a kernels of the flow-aggregation stage.
 //
-//   k_decode_aggregate<MODE,W>  fused kernel 1 -> kernel 2: length-delimited
-//                               FlowMessage bytes -> group table (+ sketch).  The
-//                               columnar intermediate never touches HBM.
-//   k_decode_columns            kernel 1 alone: bytes -> 20 decoded columns in HBM
-//                               (inserter.go:142-157 row + create.sh:36-59 columns).
-//   k_aggregate_columns<MODE>   kernel 2 alone: columns -> group table (+ sketch).
-//   k_compact_rows<KW>          flush: occupied slots -> dense fa_row array.
-//   k_estimate<KW>              sketch estimate of every group (top-K candidates).
+//   k_tile<AggConsumer<MODE,W>>  fused kernel 1 -> kernel 2: length-delimited
+//                                FlowMessage bytes -> group table (+ sketch).  The
+//                                columnar intermediate never touches HBM.
+//   k_tile<ColConsumer>          kernel 1 alone: bytes -> 20 decoded columns in HBM
+//                                (inserter.go:142-157 row + create.sh:36-59 columns).
+//   k_aggregate_columns<MODE>    kernel 2 alone: columns -> group table (+ sketch).
+//   k_table_init / k_compact_rows / k_estimate   table reset, flush, top-K candidates.
+//
+// Tile kernel: one CTA = one tile of <= 256 records.  The tile's byte span is
+// brought into shared memory by ONE bulk-async copy (cp.async.bulk, the 1-D TMA
+// path: SASS UBLKCP) signalled on an mbarrier, with an L2 evict-first policy so the
+// stream does not push the group table out of L2; then one thread parses one
+// record from shared memory.  Up to 8 CTAs are resident per SM, so copies of some
+// tiles overlap the parsing of others without any intra-CTA pipeline.
 //
 // The path is integer / memory bound: no tensor cores anywhere.
 #pragma once
@@ -20,21 +26,24 @@
 namespace fa {
 
 constexpr int kThreads = 256;            // one record per thread per tile
-constexpr int kTileRecords = kThreads;   // records per CTA tile
-constexpr int kTileBytes = 40 * 1024;    // staged bytes per tile (mean mocker tile: 21.6 KB)
-constexpr int kTilePad = 64;             // over-read slack behind the tile
+constexpr int kTilePad = 64;             // over-read slack behind the tile (then the mbarrier)
+constexpr int kTileBytesMax = 96 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 24 KB)
 
 struct Counters {
-    unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows, pad[3];
+    unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows;
+    unsigned int side_state, pad0;
+    unsigned long long pad[2];
 };
 
 struct SubmitParams {
-    const uint8_t *buf;       // device bytes; buf[0] is host/stream byte `base`
+    const uint8_t *buf;       // device bytes; buf[0] is stream byte `base`
     unsigned long long base;  // offsets[] are relative to the stream, buf to base (multiple of 16)
-    unsigned long long len;   // bytes readable behind buf (rounded up to 16 by the owner)
+    unsigned long long len;   // bytes readable behind buf (the owner pads the allocation to 16)
     const uint32_t *offsets;  // n_records + 1
     uint32_t n_records;
     uint32_t framed;
+    uint32_t tile_records;    // records per CTA tile (<= blockDim.x)
+    uint32_t tile_bytes;      // shared-memory bytes for the tile (multiple of 16); barrier sits behind it
     // group table
     uint8_t *slots;
     uint32_t slot_mask;
@@ -99,7 +108,7 @@ __device__ __forceinline__ bool make_key(const Flow &f, uint32_t *key)
     }
 }
 
-// table / sketch hash; same arithmetic as the oracle's fo_hash64
+// table / sketch hash; same arithmetic as the checker's restatement
 template <int KW>
 __device__ __forceinline__ unsigned long long hash64(const uint32_t *key)
 {
@@ -121,20 +130,44 @@ __device__ __forceinline__ unsigned long long hash64(const uint32_t *key)
 
 // ---- group table: open addressing, linear probing, in HBM (L2-resident when small) ---
 //
-// slot = { u32 state; u32 key[KW]; pad to 8; u64 bytes, packets, count }
-template <int KW> struct SlotLayout {
-    static constexpr uint32_t VAL_OFF = (4u + 4u * KW + 7u) & ~7u;
-    static constexpr uint32_t BYTES = VAL_OFF + 24u;
-};
+// Three slot layouts, all with values {u64 bytes, packets, count} behind the key:
+//   KW <= 2   32 B  { u64 key | 3 x u64 }            claimed by a 64-bit CAS on the key
+//   KW == 4   48 B  { u128 key | 3 x u64 | pad }     claimed by a 128-bit CAS on the key
+//   KW == 11  72 B  { u32 state, u32 key[11] | 3 x u64 }   claimed through a state word
+// For the CAS layouts the all-ones key marks an empty slot; the one real key that
+// is all ones lives in a reserved side slot behind the table (index = capacity).
+// One 32-byte sector per record for the AS-pair roll-up.  Lookups are relaxed
+// GPU-scope loads served by L2 (no L1 invalidation on the hot path).
+template <int KW> struct SlotLayout;
+template <> struct SlotLayout<1> { static constexpr uint32_t BYTES = 32, VAL_OFF = 8; };
+template <> struct SlotLayout<2> { static constexpr uint32_t BYTES = 32, VAL_OFF = 8; };
+template <> struct SlotLayout<4> { static constexpr uint32_t BYTES = 48, VAL_OFF = 16; };
+template <> struct SlotLayout<11> { static constexpr uint32_t BYTES = 72, VAL_OFF = 48; };
 enum : uint32_t { SLOT_EMPTY = 0, SLOT_BUSY = 1, SLOT_READY = 2 };
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const void *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const void *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ld_relaxed_u128(const void *p, unsigned long long &lo, unsigned long long &hi)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const void *p)
 {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+__device__ __forceinline__ void st_release_u32(void *p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -142,47 +175,112 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
 {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void cas_u128(void *p, unsigned long long cmp_lo, unsigned long long cmp_hi, unsigned long long new_lo,
+                                         unsigned long long new_hi, unsigned long long &old_lo, unsigned long long &old_hi)
+{
+    asm volatile(
+        "{\n\t.reg .b128 c, s, d;\n\t"
+        "mov.b128 c, {%3, %4};\n\t"
+        "mov.b128 s, {%5, %6};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 d, [%2], c, s;\n\t"
+        "mov.b128 {%0, %1}, d;\n\t}"
+        : "=l"(old_lo), "=l"(old_hi)
+        : "l"(p), "l"(cmp_lo), "l"(cmp_hi), "l"(new_lo), "l"(new_hi)
+        : "memory");
+}
 
-// sum(Bytes), sum(Packets), count() for one flow (create.sh:105-107).  UInt64
-// wrap-around is native to the 64-bit reduction.
+__device__ __forceinline__ void slot_add(uint8_t *vals, unsigned long long bytes, unsigned long long packets, unsigned long long count)
+{
+    // sum(Bytes), sum(Packets), count(): create.sh:105-107; UInt64 wrap-around is native
+    unsigned long long *v = reinterpret_cast<unsigned long long *>(vals);
+    red_add_u64(v + 0, bytes);
+    red_add_u64(v + 1, packets);
+    red_add_u64(v + 2, count);
+}
+
+template <int KW>
+__device__ __forceinline__ void side_slot_add(const SubmitParams &p, unsigned long long bytes, unsigned long long packets,
+                                              unsigned long long count)
+{
+    uint8_t *s = p.slots + ((size_t)p.slot_mask + 1) * SlotLayout<KW>::BYTES;
+    if (atomicCAS(&p.counters->side_state, 0u, 1u) == 0u) atomicAdd(&p.counters->n_groups, 1ull);
+    slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+}
+
 template <int KW>
 __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t *key, unsigned long long h,
-                                          unsigned long long bytes, unsigned long long packets,
-                                          unsigned long long count)
+                                          unsigned long long bytes, unsigned long long packets, unsigned long long count)
 {
     uint32_t slot = (uint32_t)(h >> 32) & p.slot_mask;
-    for (uint32_t probe = 0; probe <= p.slot_mask; probe++) {
-        uint8_t *s = p.slots + (size_t)slot * SlotLayout<KW>::BYTES;
-        uint32_t *state = reinterpret_cast<uint32_t *>(s);
-        uint32_t *skey = state + 1;
-        uint32_t st = ld_acquire_u32(state);
-        if (st == SLOT_EMPTY) {
-            const uint32_t old = atomicCAS(state, (uint32_t)SLOT_EMPTY, (uint32_t)SLOT_BUSY);
-            if (old == SLOT_EMPTY) {
+    if (KW <= 2) {
+        const unsigned long long k = (unsigned long long)key[0] | (KW == 2 ? (unsigned long long)key[1] << 32 : 0ull);
+        if (k == ~0ull) return side_slot_add<KW>(p, bytes, packets, count);
+#pragma unroll 1
+        for (uint32_t probe = 0; probe <= p.slot_mask; probe++) {
+            uint8_t *s = p.slots + (size_t)slot * SlotLayout<KW>::BYTES;
+            unsigned long long cur = ld_relaxed_u64(s);
+            if (cur == ~0ull) {
+                cur = atomicCAS(reinterpret_cast<unsigned long long *>(s), ~0ull, k);
+                if (cur == ~0ull) {
+                    atomicAdd(&p.counters->n_groups, 1ull);
+                    cur = k;
+                }
+            }
+            if (cur == k) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+            slot = (slot + 1) & p.slot_mask;
+        }
+    } else if (KW == 4) {
+        const unsigned long long klo = (unsigned long long)key[0] | ((unsigned long long)key[1] << 32);
+        const unsigned long long khi = (unsigned long long)key[2] | ((unsigned long long)key[3] << 32);
+        if ((klo & khi) == ~0ull) return side_slot_add<KW>(p, bytes, packets, count);
+#pragma unroll 1
+        for (uint32_t probe = 0; probe <= p.slot_mask; probe++) {
+            uint8_t *s = p.slots + (size_t)slot * SlotLayout<KW>::BYTES;
+            unsigned long long clo, chi;
+            ld_relaxed_u128(s, clo, chi);  // one 16-byte access: a consistent snapshot of the key
+            if ((clo & chi) == ~0ull) {
+                cas_u128(s, ~0ull, ~0ull, klo, khi, clo, chi);
+                if ((clo & chi) == ~0ull) {
+                    atomicAdd(&p.counters->n_groups, 1ull);
+                    clo = klo;
+                    chi = khi;
+                }
+            }
+            if (clo == klo && chi == khi) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+            slot = (slot + 1) & p.slot_mask;
+        }
+    } else {
+        // wide keys (5-tuple): EMPTY -> BUSY (CAS) -> key written -> READY (release).  A reader
+        // that sees READY through a relaxed load re-reads with acquire only when it has to
+        // decide a MISmatch on a key it may have read before it was published.
+#pragma unroll 1
+        for (uint32_t probe = 0; probe <= p.slot_mask; probe++) {
+            uint8_t *s = p.slots + (size_t)slot * SlotLayout<KW>::BYTES;
+            uint32_t *state = reinterpret_cast<uint32_t *>(s);
+            uint32_t *skey = state + 1;
+            uint32_t st = ld_relaxed_u32(state);
+            if (st == SLOT_EMPTY) {
+                const uint32_t old = atomicCAS(state, (uint32_t)SLOT_EMPTY, (uint32_t)SLOT_BUSY);
+                if (old == SLOT_EMPTY) {
 #pragma unroll
-                for (int i = 0; i < KW; i++) skey[i] = key[i];
-                st_release_u32(state, SLOT_READY);
-                atomicAdd(&p.counters->n_groups, 1ull);
-                st = SLOT_READY;
-            } else {
+                    for (int i = 0; i < KW; i++) skey[i] = key[i];
+                    st_release_u32(state, SLOT_READY);
+                    atomicAdd(&p.counters->n_groups, 1ull);
+                    return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+                }
                 st = old;
             }
-        }
-        while (st == SLOT_BUSY) {  // another thread is publishing this slot's key
-            __nanosleep(32);
-            st = ld_acquire_u32(state);
-        }
-        bool same = true;
+            while (st != SLOT_READY) {  // another thread is publishing this slot's key
+                __nanosleep(32);
+                st = ld_acquire_u32(state);
+            }
+            // state READY was observed before these loads are issued (dependent branch above)
+            bool same = true;
 #pragma unroll
-        for (int i = 0; i < KW; i++) same &= (skey[i] == key[i]);
-        if (same) {
-            unsigned long long *val = reinterpret_cast<unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
-            red_add_u64(val + 0, bytes);
-            red_add_u64(val + 1, packets);
-            red_add_u64(val + 2, count);
-            return;
+            for (int i = 0; i < KW; i++) same &= (ld_relaxed_u32(skey + i) == key[i]);
+            if (same) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+            slot = (slot + 1) & p.slot_mask;
         }
-        slot = (slot + 1) & p.slot_mask;
     }
     atomicAdd(&p.counters->n_dropped, count);
 }
@@ -217,73 +315,176 @@ __device__ __forceinline__ void aggregate_flow(const SubmitParams &p, const Flow
     if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
 }
 
-// ---- tile staging -------------------------------------------------------------------------
+// ---- tile staging: one bulk-async copy per tile ----------------------------------------------
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (1-D TMA), completion on the mbarrier, L2 evict-first
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
 }
 
 struct TileInfo {
-    uint32_t r0, n;      // first record, record count
-    uint32_t b0, b1;     // stream byte span of the tile
-    uint32_t a0;         // b0 rounded down to 16
-    bool staged;         // bytes [a0, b1) are in shared memory
+    uint32_t r0, n;   // first record, record count
+    uint32_t b0;      // stream byte of the tile's first record
+    uint32_t a0;      // b0 rounded down to 16: stream byte of shared-memory byte 0
+    uint32_t s_end;   // stream byte one past the staged range (a0 if nothing is staged)
 };
 
-// Stage the byte span of records [r0, r0+n) into shared memory with coalesced
-// 16-byte streaming loads.  Falls back (staged=false) when the span is not sane
-// or does not fit.
-__device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t tile, uint32_t *smem_words)
+// Stage as much of the byte span of records [r0, r0+n) as fits into shared memory.
+// Records that end beyond s_end (oversized tiles, out-of-order offsets) are parsed
+// from global memory instead.
+__device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t tile, uint8_t *smem)
 {
     TileInfo t;
-    t.r0 = tile * kTileRecords;
-    t.n = min((uint32_t)kTileRecords, p.n_records - t.r0);
+    t.r0 = tile * p.tile_records;
+    t.n = min(p.tile_records, p.n_records - t.r0);
     t.b0 = __ldg(p.offsets + t.r0);
-    t.b1 = __ldg(p.offsets + t.r0 + t.n);
+    const uint32_t b1 = __ldg(p.offsets + t.r0 + t.n);
     t.a0 = t.b0 & ~15u;
     const unsigned long long end = p.base + p.len;
-    t.staged = t.b0 <= t.b1 && t.b0 >= p.base && (unsigned long long)t.b1 <= end && (t.b1 - t.a0) <= (uint32_t)kTileBytes;
-    if (t.staged) {
-        const uint32_t n16 = (t.b1 - t.a0 + 15u) >> 4;
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.buf + ((unsigned long long)t.a0 - p.base));
-        uint4 *dst = reinterpret_cast<uint4 *>(smem_words);
-        for (uint32_t i = threadIdx.x; i < n16; i += kThreads) dst[i] = ldg_stream(src + i);
-    }
+    const bool sane = t.b0 <= b1 && t.b0 >= p.base && (unsigned long long)b1 <= end;
+    uint32_t nbytes = 0;
+    if (sane) nbytes = min((b1 - t.a0 + 15u) & ~15u, p.tile_bytes);
+    t.s_end = t.a0 + nbytes;
+    const uint32_t bar = smem_u32(smem + p.tile_bytes + kTilePad);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        if (nbytes) {
+            mbar_expect_tx(bar, nbytes);
+            bulk_load(smem_u32(smem), p.buf + ((unsigned long long)t.a0 - p.base), nbytes, bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    }
     return t;
 }
 
-// one record from global memory (tile too large for shared memory, or offsets
-// out of order): correct, slow, rare
-template <uint32_t NEED>
-__device__ __noinline__ bool decode_record_global(const SubmitParams &p, uint32_t o0, uint32_t o1, Flow &f)
+// ---- consumers ----------------------------------------------------------------------------------
+
+struct Columns {
+    uint8_t *valid;
+    unsigned long long *time_received, *time_flow_start, *sampling_rate, *bytes, *packets;
+    uint32_t *type, *sequence_num, *src_as, *dst_as, *etype, *proto, *src_port, *dst_port;
+    uint4 *src_addr, *dst_addr, *sampler_addr;
+    uint8_t *src_addr_len, *dst_addr_len, *sampler_addr_len;
+};
+
+struct TileParams {
+    SubmitParams p;
+    Columns c;  // only read by ColConsumer
+};
+
+template <int MODE, bool WEIGHTED>
+struct AggConsumer {
+    static constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
+    static constexpr int MIN_BLOCKS = KeyTraits<MODE>::KW <= 4 ? 8 : 5;  // 32 / 48 registers per thread
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey)
+    {
+        if (ok) {
+            if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
+            aggregate_flow<MODE>(tp.p, f, nokey);
+        } else {
+            bad++;  // inserter.go:125-126: log, skip the row
+        }
+    }
+};
+
+__device__ __forceinline__ uint4 addr_bytes(const uint32_t be[4])
 {
-    const unsigned long long end = p.base + p.len;
-    if (o0 > o1 || o0 < p.base || (unsigned long long)o1 > end) return false;
-    if (o0 == o1) return p.framed == 0;  // empty bare message decodes to all-zero; empty framed span is bad
-    ByteSrc s;
-    s.words = reinterpret_cast<const uint32_t *>(p.buf);
-    s.limit_word = (uint32_t)(((p.len + 15ull) & ~15ull) / 4ull) - 1u;
-    return decode_record<NEED>(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, f);
+    // big-endian words back to memory byte order
+    return make_uint4(__byte_perm(be[0], 0, 0x0123), __byte_perm(be[1], 0, 0x0123), __byte_perm(be[2], 0, 0x0123),
+                      __byte_perm(be[3], 0, 0x0123));
 }
 
-template <uint32_t NEED>
-__device__ __forceinline__ bool decode_tile_record(const SubmitParams &p, const TileInfo &t, const uint32_t *smem_words,
-                                                   uint32_t r, Flow &f)
-{
-    const uint32_t o0 = __ldg(p.offsets + r), o1 = __ldg(p.offsets + r + 1);
-    flow_reset(f);
-    if (t.staged && o0 >= t.b0 && o1 <= t.b1 && o0 <= o1) {
-        SmemSrc s;
-        s.words = smem_words;
-        return decode_record<NEED>(s, o0 - t.a0, o1 - t.a0, p.framed != 0, f);
+struct ColConsumer {
+    static constexpr uint32_t NEED = F_ALL;
+    static constexpr int MIN_BLOCKS = 4;  // all 16 fields live: 64 registers per thread
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &)
+    {
+        const Columns &c = tp.c;
+        if (!ok) {
+            flow_reset(f);
+            bad++;
+        }
+        c.valid[r] = ok ? 1 : 0;
+        c.time_received[r] = f.time_received;
+        c.time_flow_start[r] = f.time_flow_start;
+        c.sampling_rate[r] = f.sampling_rate;
+        c.bytes[r] = f.bytes;
+        c.packets[r] = f.packets;
+        c.type[r] = f.type;
+        c.sequence_num[r] = f.sequence_num;
+        c.src_as[r] = f.src_as;
+        c.dst_as[r] = f.dst_as;
+        c.etype[r] = f.etype;
+        c.proto[r] = f.proto;
+        c.src_port[r] = f.src_port;
+        c.dst_port[r] = f.dst_port;
+        c.src_addr[r] = addr_bytes(f.src);
+        c.dst_addr[r] = addr_bytes(f.dst);
+        c.sampler_addr[r] = addr_bytes(f.sampler);
+        c.src_addr_len[r] = (uint8_t)min(f.src_len, 255u);
+        c.dst_addr_len[r] = (uint8_t)min(f.dst_len, 255u);
+        c.sampler_addr_len[r] = (uint8_t)min(f.sampler_len, 255u);
     }
-    return decode_record_global<NEED>(p, o0, o1, f);
+};
+
+// one record straight from global memory (it did not fit the staged tile, or its
+// offsets are out of order): correct, slow, rare.  Out of line with its own Flow so
+// the hot path keeps its Flow in registers.
+// Returns bad | nokey << 1.
+template <class Consumer>
+__device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32_t r, uint32_t o0, uint32_t o1)
+{
+    uint32_t bad = 0, nokey = 0;
+    const SubmitParams &p = tp.p;
+    const unsigned long long end = p.base + p.len;
+    Flow f;
+    flow_reset(f);
+    bool ok;
+    if (o0 > o1 || o0 < p.base || (unsigned long long)o1 > end) {
+        ok = false;
+    } else if (o0 == o1) {
+        ok = p.framed == 0;  // empty bare message decodes to all-zero; an empty framed span is bad
+    } else {
+        ByteSrc s;
+        s.words = reinterpret_cast<const uint32_t *>(p.buf);
+        s.limit_word = (uint32_t)(((p.len + 15ull) & ~15ull) / 4ull) - 1u;
+        ok = decode_record<Consumer::NEED>(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, f);
+    }
+    Consumer::consume(tp, r, ok, f, bad, nokey);
+    return bad | (nokey << 1);
 }
 
 __device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad, uint32_t nokey)
@@ -296,85 +497,38 @@ __device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad
     }
 }
 
-// ---- fused decode + aggregate --------------------------------------------------------------
+// ---- the tile kernel: decode (+ consume) one tile per CTA ------------------------------------
 
-template <int MODE, bool WEIGHTED>
-__global__ void __launch_bounds__(kThreads) k_decode_aggregate(const SubmitParams p, const uint32_t n_tiles)
+template <class Consumer>
+__global__ void __launch_bounds__(kThreads, Consumer::MIN_BLOCKS) k_tile(const __grid_constant__ TileParams tp)
 {
-    extern __shared__ __align__(16) uint32_t smem_words[];
-    constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
+    extern __shared__ __align__(128) uint8_t smem[];
+    const SubmitParams &p = tp.p;
+    const TileInfo t = stage_tile(p, blockIdx.x, smem);
     uint32_t bad = 0, nokey = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileInfo t = stage_tile(p, tile, smem_words);
-        if (threadIdx.x < t.n) {
+    const bool active = threadIdx.x < t.n;
+    const uint32_t r = t.r0 + threadIdx.x;
+    uint32_t o0 = 0, o1 = 0;
+    if (active) {  // coalesced; in flight while the bulk copy lands
+        o0 = __ldg(p.offsets + r);
+        o1 = __ldg(p.offsets + r + 1);
+    }
+    mbar_wait(smem_u32(smem + p.tile_bytes + kTilePad), 0);
+    if (active) {
+        if (o0 >= t.b0 && o0 <= o1 && o1 <= t.s_end) {
             Flow f;
-            if (decode_tile_record<NEED>(p, t, smem_words, t.r0 + threadIdx.x, f)) {
-                if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-                aggregate_flow<MODE>(p, f, nokey);
-            } else {
-                bad++;  // inserter.go:125-126: log, skip the row
-            }
+            flow_reset(f);
+            SmemSrc s;
+            s.base = smem_u32(smem);
+            const bool ok = decode_record<Consumer::NEED>(s, o0 - t.a0, o1 - t.a0, p.framed != 0, f);
+            Consumer::consume(tp, r, ok, f, bad, nokey);
+        } else {
+            const uint32_t res = record_from_global<Consumer>(tp, r, o0, o1);
+            bad += res & 1u;
+            nokey += res >> 1;
         }
-        __syncthreads();  // tile buffer is reused
     }
     flush_counts(p, bad, nokey);
-}
-
-// ---- kernel 1 alone: decode to columns -------------------------------------------------------
-
-struct Columns {
-    uint8_t *valid;
-    unsigned long long *time_received, *time_flow_start, *sampling_rate, *bytes, *packets;
-    uint32_t *type, *sequence_num, *src_as, *dst_as, *etype, *proto, *src_port, *dst_port;
-    uint4 *src_addr, *dst_addr, *sampler_addr;
-    uint8_t *src_addr_len, *dst_addr_len, *sampler_addr_len;
-};
-
-__device__ __forceinline__ uint4 addr_bytes(const uint32_t be[4])
-{
-    // big-endian words back to memory byte order
-    return make_uint4(__byte_perm(be[0], 0, 0x0123), __byte_perm(be[1], 0, 0x0123), __byte_perm(be[2], 0, 0x0123),
-                      __byte_perm(be[3], 0, 0x0123));
-}
-
-__global__ void __launch_bounds__(kThreads) k_decode_columns(const SubmitParams p, const uint32_t n_tiles, const Columns c)
-{
-    extern __shared__ __align__(16) uint32_t smem_words[];
-    uint32_t bad = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileInfo t = stage_tile(p, tile, smem_words);
-        if (threadIdx.x < t.n) {
-            const uint32_t r = t.r0 + threadIdx.x;
-            Flow f;
-            const bool ok = decode_tile_record<F_ALL>(p, t, smem_words, r, f);
-            if (!ok) {
-                flow_reset(f);
-                bad++;
-            }
-            c.valid[r] = ok ? 1 : 0;
-            c.time_received[r] = f.time_received;
-            c.time_flow_start[r] = f.time_flow_start;
-            c.sampling_rate[r] = f.sampling_rate;
-            c.bytes[r] = f.bytes;
-            c.packets[r] = f.packets;
-            c.type[r] = f.type;
-            c.sequence_num[r] = f.sequence_num;
-            c.src_as[r] = f.src_as;
-            c.dst_as[r] = f.dst_as;
-            c.etype[r] = f.etype;
-            c.proto[r] = f.proto;
-            c.src_port[r] = f.src_port;
-            c.dst_port[r] = f.dst_port;
-            c.src_addr[r] = addr_bytes(f.src);
-            c.dst_addr[r] = addr_bytes(f.dst);
-            c.sampler_addr[r] = addr_bytes(f.sampler);
-            c.src_addr_len[r] = (uint8_t)min(f.src_len, 255u);
-            c.dst_addr_len[r] = (uint8_t)min(f.dst_len, 255u);
-            c.sampler_addr_len[r] = (uint8_t)min(f.sampler_len, 255u);
-        }
-        __syncthreads();
-    }
-    flush_counts(p, bad, 0);
 }
 
 // ---- kernel 2 alone: columns -> table / sketch -------------------------------------------------
@@ -415,21 +569,59 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
     flush_counts(p, 0, nokey);
 }
 
-// ---- flush: occupied slots -> dense rows -------------------------------------------------------
+// ---- table reset / flush / top-K candidates ----------------------------------------------------------
+
+// empty table: all-ones keys (CAS layouts) or state 0 (wide keys), zero values; n_slots includes the side slot
+template <int KW>
+__global__ void __launch_bounds__(256) k_table_init(uint8_t *slots, unsigned long long n_slots)
+{
+    constexpr uint32_t WORDS = SlotLayout<KW>::BYTES / 8;
+    constexpr uint32_t KEY_WORDS64 = KW <= 2 ? 1 : (KW == 4 ? 2 : 0);
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(slots);
+    const unsigned long long total = n_slots * WORDS;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x)
+        w[i] = (i % WORDS) < KEY_WORDS64 ? ~0ull : 0ull;
+}
 
 template <int KW>
-__global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, uint32_t n_slots, fa_row *rows,
+__device__ __forceinline__ bool slot_read(const uint8_t *s, bool is_side, uint32_t *key)
+{
+    if (KW <= 2) {
+        const unsigned long long k = *reinterpret_cast<const unsigned long long *>(s);
+        key[0] = (uint32_t)k;
+        if (KW == 2) key[1] = (uint32_t)(k >> 32);
+        const unsigned long long cnt = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF)[2];
+        return is_side ? cnt != 0 : k != ~0ull;
+    } else if (KW == 4) {
+        const unsigned long long lo = reinterpret_cast<const unsigned long long *>(s)[0], hi = reinterpret_cast<const unsigned long long *>(s)[1];
+        key[0] = (uint32_t)lo; key[1] = (uint32_t)(lo >> 32); key[2] = (uint32_t)hi; key[3] = (uint32_t)(hi >> 32);
+        const unsigned long long cnt = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF)[2];
+        return is_side ? cnt != 0 : (lo & hi) != ~0ull;
+    } else {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
+#pragma unroll
+        for (int k = 0; k < KW; k++) key[k] = w[1 + k];
+        return !is_side && w[0] == SLOT_READY;
+    }
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsigned long long n_slots, fa_row *rows,
                                                       unsigned long long cap, Counters *counters)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
-        const uint8_t *s = slots + (size_t)i * SlotLayout<KW>::BYTES;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
-        if (w[0] != SLOT_READY) continue;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
+        uint32_t key[KW];
+        if (!slot_read<KW>(s, i == n_slots - 1, key)) continue;
+        if (i == n_slots - 1) {  // the side slot holds the all-ones key
+#pragma unroll
+            for (int k = 0; k < KW; k++) key[k] = 0xFFFFFFFFu;
+        }
         const unsigned long long at = atomicAdd(&counters->flush_rows, 1ull);
         if (at >= cap) continue;
         fa_row r;
 #pragma unroll
-        for (int k = 0; k < FA_MAX_KEY_WORDS; k++) r.key[k] = k < KW ? w[1 + k] : 0u;
+        for (int k = 0; k < FA_MAX_KEY_WORDS; k++) r.key[k] = k < KW ? key[k] : 0u;
         const unsigned long long *v = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
         r.bytes = v[0];
         r.packets = v[1];
@@ -438,20 +630,20 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, uint
     }
 }
 
-// ---- sketch estimate of every group (top-K candidates) -------------------------------------------
-
+// sketch estimate of every group (top-K candidates)
 template <int KW>
-__global__ void __launch_bounds__(256) k_estimate(const uint8_t *slots, uint32_t n_slots, const unsigned long long *cms,
+__global__ void __launch_bounds__(256) k_estimate(const uint8_t *slots, unsigned long long n_slots, const unsigned long long *cms,
                                                   uint32_t depth, uint32_t wlog2, fa_hh *out, unsigned long long cap,
                                                   Counters *counters)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
-        const uint8_t *s = slots + (size_t)i * SlotLayout<KW>::BYTES;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
-        if (w[0] != SLOT_READY) continue;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
         uint32_t key[KW];
+        if (!slot_read<KW>(s, i == n_slots - 1, key)) continue;
+        if (i == n_slots - 1) {
 #pragma unroll
-        for (int k = 0; k < KW; k++) key[k] = w[1 + k];
+            for (int k = 0; k < KW; k++) key[k] = 0xFFFFFFFFu;
+        }
         const unsigned long long h = hash64<KW>(key);
         const uint32_t a = (uint32_t)h, b = (uint32_t)(h >> 32) | 1u, mask = (1u << wlog2) - 1u;
         unsigned long long est = ~0ull;

@@ -238,15 +238,19 @@ class FlowAgg:
 
     # -- emit (inserter.go:90-111 -> flows_5m rows, create.sh:70-110)
     def flush(self, keep=False, sort=True, allow_full=False):
-        n = C.c_size_t()
         flags = (FA_FLUSH_KEEP if keep else 0) | (0 if sort else FA_FLUSH_UNSORTED)
-        rc = self._L.fa_flush(self._h, None, 0, C.byref(n), FA_FLUSH_KEEP)
-        if rc not in (0, -4, -5):
-            self._check(rc, "fa_flush")
-        rows = np.zeros(n.value, dtype=ROW_DTYPE)
         ok = (0, -5) if allow_full else (0,)
-        self._check(self._L.fa_flush(self._h, rows.ctypes.data if n.value else None, n.value, C.byref(n), flags), "fa_flush", ok)
-        return rows
+        n = C.c_size_t()
+        cap = getattr(self, "_rows_cap", 1 << 16)
+        while True:
+            rows = np.empty(cap, dtype=ROW_DTYPE)
+            rc = self._L.fa_flush(self._h, rows.ctypes.data, cap, C.byref(n), flags)
+            if rc == -4 and n.value > cap:  # FA_ERR_CAPACITY: nothing was reset, retry with the size it reported
+                cap = n.value
+                continue
+            self._check(rc, "fa_flush", ok)
+            self._rows_cap = max(cap, 1 << 16)
+            return rows[: n.value]
 
     def reset(self):
         self._check(self._L.fa_reset(self._h), "fa_reset")
