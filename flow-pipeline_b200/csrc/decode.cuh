@@ -89,7 +89,7 @@ struct SmemSrc {
     // bytes pos..pos+7 as little-endian (lo, hi)
     __device__ __forceinline__ void window(uint32_t pos, uint32_t &lo, uint32_t &hi) const
     {
-        const uint32_t a = base + (pos & ~3u), sh = (pos & 3u) * 8u;
+        const uint32_t a = base + (pos & ~3u), sh = pos * 8u;  // the funnel shift uses sh mod 32
         uint32_t w0, w1, w2;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
         asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
@@ -259,80 +259,116 @@ __device__ __forceinline__ void load_addr(const Src s, uint32_t pos, uint32_t le
     }
 }
 
-// varint whose bytes start at bit 0 of (xlo, xhi): <= 5 bytes decoded branch-free.
-// Returns the byte count (0 = longer than 5 bytes: take the slow path).
-__device__ __forceinline__ uint32_t varint5(uint32_t xlo, uint32_t xhi, unsigned long long &v)
+// which varint field numbers a kernel reads: bit n of (m1:m0) = field n
+__host__ __device__ constexpr uint32_t need_mask_lo(uint32_t need)
 {
-    const uint32_t stop = ~xlo & 0x80808080u;              // terminator bytes among the first four
-    const uint32_t t = __ffs(stop);                        // 8,16,24,32, or 0 if none
-    const bool five = stop == 0u;
-    const uint32_t keep = five ? 0xFFFFFFFFu : (0xFFFFFFFFu >> ((32u - t) & 31u));
-    const uint32_t x = xlo & keep;
-    const uint32_t low28 = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
-    const uint32_t b4 = five ? (xhi & 0x7fu) : 0u;        // fifth byte: bits 28..34
-    v = ((unsigned long long)(b4 >> 4) << 32) | (unsigned long long)(low28 | (b4 << 28));
-    if (five && (xhi & 0x80u)) return 0u;                  // six bytes or more
-    return five ? 5u : (t >> 3);
+    return ((need & F_TYPE) ? 1u << 1 : 0u) | ((need & F_TIME_RECEIVED) ? 1u << 2 : 0u) | ((need & F_SAMPLING_RATE) ? 1u << 3 : 0u) |
+           ((need & F_SEQUENCE_NUM) ? 1u << 4 : 0u) | ((need & F_BYTES) ? 1u << 9 : 0u) | ((need & F_PACKETS) ? 1u << 10 : 0u) |
+           ((need & F_SRC_AS) ? 1u << 14 : 0u) | ((need & F_DST_AS) ? 1u << 15 : 0u) | ((need & F_PROTO) ? 1u << 20 : 0u) |
+           ((need & F_SRC_PORT) ? 1u << 21 : 0u) | ((need & F_DST_PORT) ? 1u << 22 : 0u) | ((need & F_ETYPE) ? 1u << 30 : 0u);
+}
+__host__ __device__ constexpr uint32_t need_mask_hi(uint32_t need) { return (need & F_TIME_FLOW_START) ? 1u << (38 - 32) : 0u; }
+
+template <uint32_t NEED>
+__device__ __forceinline__ bool varint_field_needed(uint32_t num)
+{
+    constexpr uint32_t M0 = need_mask_lo(NEED), M1 = need_mask_hi(NEED);
+    // funnel shift with clamp: a shift of 32 or more yields 0, so out-of-range numbers are "not needed"
+    uint32_t bit = __funnelshift_rc(M0, 0u, num);
+    if (M1 != 0u) bit = num < 32u ? bit : __funnelshift_rc(M1, 0u, num - 32u);
+    return (bit & 1u) != 0u;
+}
+
+// everything that is neither a varint nor length-delimited: fixed32/fixed64 skips, group skips,
+// and the error cases.  Returns the new position, 0xFFFFFFFF on error.
+template <class Src>
+__device__ __noinline__ uint32_t skip_other(const Src s, uint32_t pos, uint32_t end, uint32_t wt, uint32_t num)
+{
+    if (pos > end) return 0xFFFFFFFFu;
+    if (wt == 5) return end - pos < 4 ? 0xFFFFFFFFu : pos + 4;
+    if (wt == 1) return end - pos < 8 ? 0xFFFFFFFFu : pos + 8;
+    if (wt == 3) return skip_group(s, pos, end, num);
+    return 0xFFFFFFFFu;  // end-group at top level, or wire type 6/7
 }
 
 // ---- the decoder -------------------------------------------------------------------
 
+#define FA_POS_ERR 0xFFFFFFFFu
+
 // Decode the message occupying [pos,end) of the source.  Returns true when
 // proto.Unmarshal would return nil.  `f` must be zero-initialised (m.Reset()).
+// Errors park pos at FA_POS_ERR, which ends the loop; the record is good iff the
+// loop ends exactly on `end`.  Values written by a record that is then rejected are
+// never looked at.
 template <uint32_t NEED, class Src>
 __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const uint32_t end, Flow &f)
 {
     while (pos < end) {
         uint32_t lo, hi;
         s.window(pos, lo, hi);
-        // ---- tag: 1 or 2 bytes branch-free ----
-        uint32_t tag, tn;
-        if ((lo & 0x8080u) == 0x8080u) {  // three bytes or more: rare (field numbers >= 2048)
-            const VarintRes t = varint_slow(s, pos, end);
-            if (!t.n || (t.v >> 3) > 0x1fffffffull) return false;
-            tag = (uint32_t)t.v;
-            pos += t.n;
-            s.window(pos, lo, hi);  // re-centre the window on the value
-            tn = 0;
+        uint32_t num, wt, xlo, xhi;
+        if (!(lo & 0x80u)) {
+            // 1-byte tag: fields 1..15 (9 of the 13 fields every producer sends)
+            wt = lo & 7u;
+            num = (lo >> 3) & 0xfu;
+            pos += 1u;
+            xlo = __funnelshift_r(lo, hi, 8);
+            xhi = hi >> 8;
+        } else if (!(lo & 0x8000u)) {
+            // 2-byte tag: fields 16..2047
+            const uint32_t tag = (lo & 0x7fu) | ((lo >> 1) & 0x3f80u);
+            wt = tag & 7u;
+            num = tag >> 3;
+            pos += 2u;
+            xlo = __funnelshift_r(lo, hi, 16);
+            xhi = hi >> 16;
         } else {
-            const bool one = !(lo & 0x80u);
-            tag = one ? (lo & 0x7fu) : ((lo & 0x7fu) | ((lo >> 1) & 0x3f80u));
-            tn = one ? 1u : 2u;
-        }
-        const uint32_t num = tag >> 3, wt = tag & 7u;
-        if (num == 0) return false;
-        pos += tn;
-        // value window: bytes pos.. (at least 6 valid)
-        const uint32_t sh = tn * 8u;
-        const uint32_t xlo = __funnelshift_r(lo, hi, sh);
-        const uint32_t xhi = hi >> sh;
-        if (wt == 0) {
-            // ---- varint ----
-            unsigned long long v;
-            uint32_t vn = varint5(xlo, xhi, v);
-            if (vn == 0) {
-                const VarintRes r = varint_slow(s, pos, end);
-                if (!r.n) return false;
-                v = r.v;
-                vn = r.n;
+            // three bytes or more: field numbers >= 2048 or an over-long encoding (rare)
+            const VarintRes t = varint_slow(s, pos, end);
+            if (!t.n || (t.v >> 3) > 0x1fffffffull) {
+                pos = FA_POS_ERR;
+                continue;
             }
-            pos += vn;
-            if (pos > end) return false;  // tag or value ran past the end of the record
-            store_varint_field<NEED>(f, num, v);
+            wt = (uint32_t)t.v & 7u;
+            num = (uint32_t)(t.v >> 3);
+            pos += t.n;
+            s.window(pos, xlo, xhi);  // the window restarts on the value
+        }
+        // xlo/xhi: bytes pos.. (at least 6 valid)
+        if (__builtin_expect(wt == 0, 1)) {
+            // ---- varint ----
+            const uint32_t stop = ~xlo & 0x80808080u;  // terminator bytes among the first four
+            if (__builtin_expect(stop == 0u && (xhi & 0x80u) != 0u, 0)) {
+                const VarintRes r = varint_slow(s, pos, end);  // six bytes or more
+                pos = r.n ? pos + r.n : FA_POS_ERR;
+                store_varint_field<NEED>(f, num, r.v);
+            } else {
+                const uint32_t t = __ffs(stop);  // 8,16,24,32, or 0: five bytes
+                pos += stop ? (t >> 3) : 5u;
+                if (varint_field_needed<NEED>(num)) {
+                    const uint32_t keep = stop ? (0xFFFFFFFFu >> ((32u - t) & 31u)) : 0xFFFFFFFFu;
+                    const uint32_t x = xlo & keep;
+                    const uint32_t low28 = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
+                    const uint32_t b4 = stop ? 0u : (xhi & 0x7fu);  // fifth byte: bits 28..34
+                    const unsigned long long v = ((unsigned long long)(b4 >> 4) << 32) | (unsigned long long)(low28 | (b4 << 28));
+                    store_varint_field<NEED>(f, num, v);
+                }
+            }
         } else if (wt == 2) {
             // ---- length-delimited ----
-            uint32_t n, vn;
-            if (!(xlo & 0x80u)) {
-                n = xlo & 0x7fu;
-                vn = 1;
-            } else {
+            uint32_t n;
+            if (__builtin_expect((xlo & 0x80u) != 0u, 0)) {
                 const VarintRes r = varint_slow(s, pos, end);
-                if (!r.n || r.v > 0xFFFFFFFFull) return false;
                 n = (uint32_t)r.v;
-                vn = r.n;
+                pos = (r.n && r.v <= 0xFFFFFFFFull) ? pos + r.n : FA_POS_ERR;
+            } else {
+                n = xlo & 0x7fu;
+                pos += 1;
             }
-            pos += vn;
-            if (pos > end || n > end - pos) return false;
+            if (pos > end || n > end - pos) {
+                pos = FA_POS_ERR;
+                continue;
+            }
             if ((NEED & F_SRC_ADDR) && num == 6) {
                 load_addr(s, pos, n, f.src);
                 f.src_len = n;
@@ -342,25 +378,19 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
             } else if ((NEED & F_SAMPLER_ADDR) && num == 11) {
                 load_addr(s, pos, n, f.sampler);
                 f.sampler_len = n;
-            } else if (num == 100 || num == 101) {
-                if (!utf8_valid(s, pos, n)) return false;
+            } else if (__builtin_expect(num == 100 || num == 101, 0)) {
+                if (!utf8_valid(s, pos, n)) {
+                    pos = FA_POS_ERR;
+                    continue;
+                }
             }
             pos += n;
-        } else if (wt == 5) {
-            if (pos > end || end - pos < 4) return false;
-            pos += 4;
-        } else if (wt == 1) {
-            if (pos > end || end - pos < 8) return false;
-            pos += 8;
-        } else if (wt == 3) {
-            if (pos > end) return false;
-            pos = skip_group(s, pos, end, num);
-            if (pos == 0xFFFFFFFFu) return false;
         } else {
-            return false;  // end-group at top level, or wire type 6/7
+            pos = skip_other(s, pos, end, wt, num);  // FA_POS_ERR on error
         }
+        if (num == 0u) pos = FA_POS_ERR;  // field number 0 is illegal
     }
-    return true;
+    return pos == end;  // anything that ran past the end of the record is an error too
 }
 
 // Decode the record occupying [pos,end): bare message, or varint(len) || message
