@@ -1,0 +1,164 @@
+// inserter_b200.go -- SOURCE ONLY: the cgo side of the drop-in, as a maintainer of
+// cloudflare/flow-pipeline would add it next to inserter/inserter.go.  It cannot be
+// compiled in this repository's build image (no Go toolchain, no sarama); the C++
+// program in ../inserter.cc is the same loop, built and tested here, over the same
+// C ABI (include/flowagg.h).
+//
+// What changes against inserter/inserter.go:
+//   - state keeps one *C.fa_ctx per claimed partition instead of [][]interface{} and
+//     the global mutex (inserter.go:75-88, :92, :115);
+//   - buffer() memcpy's msg.Value into the library's pinned slab instead of
+//     proto.Unmarshal + append (inserter.go:113-165);
+//   - flush() emits flows_5m rows from fa_flush instead of one INSERT per flow
+//     (inserter.go:90-111);
+//   - MarkMessage moves after the slab hand-over (inserter.go:188).
+// Flags, logging, metrics endpoint, consumer-group wiring in main() stay as they are.
+//
+//go:build cgo
+
+package main
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -L${SRCDIR}/.. -lflowagg
+#include <stdlib.h>
+#include <string.h>
+#include "flowagg.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"time"
+	"unsafe"
+
+	"github.com/Shopify/sarama"
+	log "github.com/sirupsen/logrus"
+)
+
+type partitionState struct {
+	ctx     *C.fa_ctx
+	slot    C.int
+	slab    *C.uint8_t
+	offs    *C.uint32_t
+	slabCap C.size_t
+	recCap  C.size_t
+	fill    C.size_t
+	nrec    C.size_t
+	pending []*sarama.ConsumerMessage
+}
+
+func newPartitionState(device int, keyMode C.uint32_t) *partitionState {
+	var cfg C.fa_config
+	cfg.abi_version = C.FA_ABI_VERSION
+	cfg.device = C.int32_t(device)
+	cfg.key_mode = keyMode
+	ps := &partitionState{}
+	if rc := C.fa_create(&cfg, &ps.ctx); rc != C.FA_OK {
+		// no CPU fallback: the stage needs its GPU (reference style: log.Fatal, inserter.go:249)
+		log.Fatalf("fa_create: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ps.ctx)))
+	}
+	ps.acquire()
+	return ps
+}
+
+func (ps *partitionState) acquire() {
+	if rc := C.fa_host_buffer(ps.ctx, ps.slot, &ps.slab, &ps.slabCap, &ps.offs, &ps.recCap); rc != C.FA_OK {
+		log.Fatalf("fa_host_buffer: %s", C.GoString(C.fa_strerror(rc)))
+	}
+	ps.fill, ps.nrec = 0, 0
+	*ps.offs = 0
+}
+
+func (ps *partitionState) submit(session sarama.ConsumerGroupSession) {
+	if ps.nrec == 0 {
+		return
+	}
+	if rc := C.fa_submit(ps.ctx, ps.slab, ps.fill, ps.offs, C.uint32_t(ps.nrec), C.FA_FRAMED); rc != C.FA_OK {
+		log.Fatalf("fa_submit: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ps.ctx)))
+	}
+	for _, m := range ps.pending { // offsets are marked once their bytes are in the stage
+		session.MarkMessage(m, "")
+	}
+	Inserts.Add(float64(ps.nrec)) // the counter the reference registers but never increments (inserter.go:44-49)
+	ps.pending = ps.pending[:0]
+	ps.slot ^= 1
+	ps.acquire() // blocks until that slab's previous host-to-device copy has finished
+}
+
+// buffer replaces (*state).buffer (inserter.go:113-165): the decode happens on the GPU.
+func (ps *partitionState) buffer(session sarama.ConsumerGroupSession, msg *sarama.ConsumerMessage, fixedLen bool) {
+	need := C.size_t(len(msg.Value) + 10)
+	if ps.fill+need > ps.slabCap || ps.nrec >= ps.recCap {
+		ps.submit(session)
+	}
+	dst := unsafe.Add(unsafe.Pointer(ps.slab), ps.fill)
+	n := 0
+	if !fixedLen { // bare value (mocker.go:96-97): add the varint length prefix ourselves
+		l := uint64(len(msg.Value))
+		b := (*[10]byte)(dst)
+		for l >= 0x80 {
+			b[n] = byte(l) | 0x80
+			l >>= 7
+			n++
+		}
+		b[n] = byte(l)
+		n++
+	}
+	if len(msg.Value) > 0 { // sarama owns msg.Value only until the next receive: copy now
+		C.memcpy(unsafe.Add(dst, n), unsafe.Pointer(&msg.Value[0]), C.size_t(len(msg.Value)))
+	}
+	ps.fill += C.size_t(n + len(msg.Value))
+	ps.nrec++
+	*(*C.uint32_t)(unsafe.Add(unsafe.Pointer(ps.offs), uintptr(ps.nrec)*4)) = C.uint32_t(ps.fill)
+	ps.pending = append(ps.pending, msg)
+}
+
+// flush replaces (*state).flush (inserter.go:90-111): aggregate rows out, table reset.
+func (ps *partitionState) flush(session sarama.ConsumerGroupSession, sink func(rows []C.fa_row)) {
+	ps.submit(session)
+	rows := make([]C.fa_row, 1<<16)
+	var n C.size_t
+	rc := C.fa_flush(ps.ctx, &rows[0], C.size_t(len(rows)), &n, 0)
+	if rc == C.FA_ERR_CAPACITY {
+		rows = make([]C.fa_row, n)
+		rc = C.fa_flush(ps.ctx, &rows[0], n, &n, 0)
+	}
+	if rc != C.FA_OK && rc != C.FA_ERR_TABLE_FULL {
+		log.Fatalf("fa_flush: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ps.ctx)))
+	}
+	sink(rows[:n])
+}
+
+// ConsumeClaim replaces (*state).ConsumeClaim (inserter.go:176-196); sarama calls it once per
+// claimed partition, each with its own fa_ctx: no cross-goroutine lock.
+func (s *state) ConsumeClaimB200(session sarama.ConsumerGroupSession, claim sarama.ConsumerGroupClaim) error {
+	ps := newPartitionState(int(claim.Partition())%s.gpus, C.FA_KEY_FLOWS5M)
+	defer C.fa_destroy(ps.ctx)
+	timer := time.After(*FlushTime)
+	for {
+		select {
+		case message, ok := <-claim.Messages():
+			if !ok {
+				ps.flush(session, s.writeRows)
+				return nil
+			}
+			log.Debugf("%s/%d/%d\t%s\t", message.Topic, message.Partition, message.Offset, message.Key)
+			ps.buffer(session, message, s.fixedLen)
+		case <-timer:
+			ps.flush(session, s.writeRows)
+			timer = time.After(*FlushTime)
+		}
+	}
+}
+
+// writeRows is the sink: flows_5m rows (create.sh:70-87) as TSV; a Clickhouse RowBinary or
+// Postgres COPY writer plugs in here.
+func (s *state) writeRows(rows []C.fa_row) {
+	for i := range rows {
+		r := &rows[i]
+		t := time.Unix(int64(r.key[0]), 0).UTC()
+		fmt.Fprintf(s.out, "%s\t%s\t%d\t%d\t[%d]\t[%d]\t[%d]\t[%d]\t%d\t%d\t%d\n", t.Format("2006-01-02"),
+			t.Format("2006-01-02 15:04:05"), r.key[1], r.key[2], r.key[3], r.bytes, r.packets, r.count, r.bytes, r.packets, r.count)
+	}
+}

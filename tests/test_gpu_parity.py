@@ -351,3 +351,35 @@ def test_config1_full_size_properties(fp, oracle, torch_cuda):
     assert first_rows["count"].sum() == slab and (rows["count"] >= first_rows["count"]).all()
     # Bytes ~ U[0,1500), Packets ~ U[0,100): mocker.go:59-60
     assert abs(rows["bytes"].sum() / n_total - 749.5) < 0.5 and abs(rows["packets"].sum() / n_total - 49.5) < 0.05
+
+
+def test_host_inserter_mirror_rows_equal_oracle(fp, oracle, torch_cuda, tmp_path):
+    """flowagg-inserter (C++ mirror of inserter.go over the C ABI): two partitions -> flows_5m TSV."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "flow-pipeline_b200", "host", "flowagg-inserter")
+    cfg = fp.FaMockerConfig.make(seed=21, flows_per_second=40, n_src_as=5, n_dst_as=5, framed=True)
+    files, rows = [], []
+    for p in range(2):
+        buf, offs = fp.mocker_host(cfg, p * 20000, 20000)
+        f = tmp_path / f"claim{p}.bin"
+        f.write_bytes(buf.tobytes())
+        files.append(str(f))
+        want, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
+        rows.append(want)
+    out = tmp_path / "rows.tsv"
+    r = subprocess.run([exe, "-claim.file", ",".join(files), "-flush.count", "0", "-flush.dur", "1h", "-out", str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = sorted(tuple(l.split("\t")[2:5] + l.split("\t")[8:11] + [l.split("\t")[1]]) for l in out.read_text().splitlines())
+    import time
+
+    want = []
+    for part in rows:
+        for w in part:
+            ts = time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(w["key"][0])))
+            want.append((str(w["key"][1]), str(w["key"][2]), f"[{w['key'][3]}]", str(w["bytes"]), str(w["packets"]), str(w["count"]), ts))
+    assert got == sorted(want)

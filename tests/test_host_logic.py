@@ -104,3 +104,34 @@ def test_oracle_threads_agree(oracle, fp):
     r1, c1, _ = oracle.run_batch(buf, offs, key_mode="flows5m", cms=(4, 10), threads=1)
     r8, c8, _ = oracle.run_batch(buf, offs, key_mode="flows5m", cms=(4, 10), threads=8)
     assert np.array_equal(r1, r8) and np.array_equal(c1, c8)
+
+
+def test_host_inserter_mirror_flags_and_consume_loop(fp, tmp_path):
+    """The C++ mirror of inserter.go: reference flag names parse, one ConsumeClaim per partition
+    walks its claim and marks every message (dry run: no GPU here)."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "flow-pipeline_b200", "host", "flowagg-inserter")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
+    cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=20, framed=True)
+    files = []
+    for p in range(2):
+        buf, _ = fp.mocker_host(cfg, p * 3000, 3000)
+        f = tmp_path / f"claim{p}.bin"
+        f.write_bytes(buf.tobytes())
+        files.append(str(f))
+    ref_flags = ["-loglevel", "info", "-metrics.addr", ":8081", "-metrics.path", "/metrics", "-kafka.version", "2.1.1",
+                 "-kafka.topic", "flows", "-kafka.brokers", "kafka:9092", "-kafka.group", "postgres-inserter",
+                 "-flush.dur", "5s", "-flush.count", "1000", "-postgres.user", "postgres", "-postgres.pass", "x",
+                 "-postgres.host", "127.0.0.1", "-postgres.port", "5432", "-postgres.dbname", "postgres"]
+    r = subprocess.run([exe, *ref_flags, "-claim.file", ",".join(files), "-dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "6000 messages marked over 2 partitions" in r.stderr
+    assert subprocess.run([exe, "-no.such.flag", "1"], capture_output=True).returncode == 2
+    # without a GPU the real path must fail loudly, not fall back
+    import torch
+
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "-claim.file", files[0]], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
