@@ -105,11 +105,20 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_run(hbuf, hoffs, n, threads):
+def cpu_oracle_run(slabs, threads):
+    """The CPU restatement (oracle/flow_oracle.c) over host slabs [(bytes, offsets)], all threads."""
     from oracle import oracle as o
 
-    rows, _, res = o.run_batch(hbuf, hoffs[: n + 1], framed=True, key_mode="aspair", threads=threads)
-    return rows, res
+    return o.run_slabs(slabs, framed=True, key_mode="aspair", threads=threads)
+
+
+def host_slabs(fp, cfg, first, n_flows, slab):
+    """mocker-distribution input generated on the host cores, one thread per slab chunk."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = [(first + a, min(slab, n_flows - a)) for a in range(0, n_flows, slab)]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda j: fp.mocker_host(cfg, j[0], j[1]), jobs))
 
 
 def run_reference(args, rank, world):
@@ -119,12 +128,12 @@ def run_reference(args, rank, world):
     import flow_pipeline_b200 as fp
 
     cores = os.cpu_count() or 1
-    n = min(N_FLOWS, max(1 << 20, min(1 << 24, (1 << 19) * cores)))
+    n = min(args.flows, max(1 << 22, min(N_FLOWS, (1 << 20) * cores)))  # bounded sample of the same stream
     cfg = mocker_cfg(fp)
-    hbuf, hoffs = fp.mocker_host(cfg, 0, n)
+    slabs = host_slabs(fp, cfg, 0, n, 1 << 20)
     times = []
     for i in range(args.warmup + args.steps):
-        rows, res = cpu_oracle_run(hbuf, hoffs, n, cores)
+        rows, res = cpu_oracle_run(slabs, cores)
         assert res["n_bad"] == 0 and int(rows["count"].sum()) == n
         if i >= args.warmup:
             times.append(res["seconds"])
@@ -136,7 +145,7 @@ def run_reference(args, rank, world):
         "data": "synthetic", "impl": "reference",
         "config": {"workload": WORKLOAD, "flows_per_step": n, "key": "(SrcAS,DstAS)", "groups": 65536,
                    "note": "Go inserter + Clickhouse cannot run here (no Go toolchain/DB); this is the C restatement "
-                           "oracle/flow_oracle.c, all host threads, per-thread tables merged at the end"},
+                           "oracle/flow_oracle.c, all host threads, per-thread tables merged in parallel at the end"},
         "cpu_baseline": {"value": v, "unit": "flows/s", "cores": cores, "kind": "port",
                          "sample": f"{n} flows of the same stream per step, {cores} pthreads"},
         "e2e": {"value": v, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -284,20 +293,27 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_s = min(slabs[0][2], max(1 << 20, min(1 << 24, (1 << 19) * cores)))
-        offs = slabs[0][1][: n_s + 1].cpu().numpy().view(np.uint32)
-        hbuf = slabs[0][0][: int(offs[n_s])].cpu().numpy()
-        crow, cres = cpu_oracle_run(hbuf, offs, n_s, cores)      # warm
-        crow, cres = cpu_oracle_run(hbuf, offs, n_s, cores)
-        c1row, c1res = cpu_oracle_run(hbuf, offs, min(n_s, 1 << 21), 1)
-        # the GPU rows restricted to the sample must equal the CPU rows: same answer, then the timing
-        chk = fp.FlowAgg("aspair", device=local_rank, stream=stream)
-        chk.submit_device(slabs[0][0], slabs[0][1], n_s, int(offs[n_s]))
+        n_want = min(n_flows, max(1 << 22, (1 << 20) * cores))
+        hs, n_s = [], 0
+        for (d_buf, d_off, n, nb) in slabs:  # the same bytes the GPU just processed
+            if n_s >= n_want:
+                break
+            hs.append((d_buf[:nb].cpu().numpy(), d_off.cpu().numpy().view(np.uint32)))
+            n_s += n
+        cpu_oracle_run(hs, cores)  # warm
+        crow, cres = cpu_oracle_run(hs, cores)
+        m1 = min(hs[0][1].size - 1, 1 << 21)
+        c1row, c1res = cpu_oracle_run([(hs[0][0], hs[0][1][: m1 + 1])], 1)
+        # the GPU rows over the same sample must equal the CPU rows: same answer first, then the timing
+        chk = fp.FlowAgg("aspair", device=local_rank, stream=stream, table_capacity=TABLE_CAP)
+        for (d_buf, d_off, n, nb) in slabs[: len(hs)]:
+            chk.submit_device(d_buf, d_off, n, nb)
         assert np.array_equal(chk.flush(), crow), "GPU and CPU roll-ups differ"
         chk.close()
         cpu = {"value": n_s / cres["seconds"], "unit": "flows/s", "cores": cores, "kind": "port",
-               "sample": f"first {n_s} flows of the same stream, {cores} pthreads, per-thread tables merged",
-               "single_thread_value": min(n_s, 1 << 21) / c1res["seconds"]}
+               "sample": f"first {n_s} flows of the same stream, {cores} pthreads, per-thread tables merged in parallel",
+               "single_thread_value": m1 / c1res["seconds"]}
+        del hs
 
     if rank == 0:
         out = {

@@ -631,9 +631,11 @@ size_t fo_topk(const uint64_t *cms, int depth, int wlog2, int n_words, const fo_
 /* ======================================================================== */
 
 typedef struct {
-    const uint8_t *buf;
-    const uint32_t *offsets;
-    size_t lo, hi;
+    const uint8_t *const *bufs;      /* slabs (each < 4 GiB: offsets are u32) */
+    const uint32_t *const *offsets;
+    const size_t *ns;
+    int n_slabs;
+    size_t lo, hi;                   /* global record range over the concatenated slabs */
     int framed;
     fo_agg *agg;      /* thread-private */
     uint64_t *cms;    /* thread-private or NULL */
@@ -646,8 +648,15 @@ static void *worker_main(void *arg)
     worker_t *w = (worker_t *)arg;
     fo_flow f;
     uint32_t key[FO_MAX_KEY_WORDS];
-    for (size_t r = w->lo; r < w->hi; r++) {
-        int rc = fo_decode_record(w->buf, w->offsets[r], w->offsets[r + 1], w->framed, &f);
+    size_t base = 0;
+    for (int sl = 0; sl < w->n_slabs; base += w->ns[sl], sl++) {
+      size_t lo = w->lo > base ? w->lo - base : 0;
+      size_t hi = w->hi > base ? w->hi - base : 0;
+      if (hi > w->ns[sl]) hi = w->ns[sl];
+      const uint8_t *buf = w->bufs[sl];
+      const uint32_t *offs = w->offsets[sl];
+      for (size_t r = lo; r < hi; r++) {
+        int rc = fo_decode_record(buf, offs[r], offs[r + 1], w->framed, &f);
         if (rc != FO_OK) { /* inserter.go:125-126: log, skip the row */
             w->n_bad++;
             continue;
@@ -665,6 +674,39 @@ static void *worker_main(void *arg)
         if (w->agg) agg_insert(w->agg, key, b, p, 1);
         /* heavy-hitter weight: Bytes*SamplingRate (viz-ch.json:233) */
         if (w->cms) fo_cms_add(w->cms, w->depth, w->wlog2, key, w->kw, f.bytes * f.sampling_rate);
+      }
+    }
+    return NULL;
+}
+
+typedef struct {
+    worker_t *ws;
+    int n_workers, me;
+    fo_agg *out;
+    uint64_t *cms_out;
+    size_t cms_words;
+} merge_t;
+
+static void *merge_main(void *arg)
+{
+    merge_t *m = (merge_t *)arg;
+    if (m->out) {
+        for (int w = 0; w < m->n_workers; w++) {
+            fo_agg *src = m->ws[w].agg;
+            for (size_t i = 0; i < src->cap; i++) {
+                if (!src->used[i]) continue;
+                if ((fo_hash64(src->slots[i].key, src->kw) >> 40) % (uint64_t)m->n_workers != (uint64_t)m->me) continue;
+                fo_agg_add_row(m->out, &src->slots[i]);
+            }
+        }
+    }
+    if (m->cms_out) {
+        size_t lo = m->cms_words * (size_t)m->me / (size_t)m->n_workers;
+        size_t hi = m->cms_words * (size_t)(m->me + 1) / (size_t)m->n_workers;
+        for (int w = 0; w < m->n_workers; w++) {
+            const uint64_t *src = m->ws[w].cms;
+            for (size_t i = lo; i < hi; i++) m->cms_out[i] += src[i];
+        }
     }
     return NULL;
 }
@@ -679,6 +721,14 @@ static double now_s(void)
 int fo_run_batch(const uint8_t *buf, const uint32_t *offsets, size_t n, int framed, fo_agg *a,
                  uint64_t *cms, int depth, int wlog2, int n_threads, fo_batch_result *res)
 {
+    return fo_run_slabs(&buf, &offsets, &n, 1, framed, a, cms, depth, wlog2, n_threads, res);
+}
+
+int fo_run_slabs(const uint8_t *const *bufs, const uint32_t *const *offsets, const size_t *ns, int n_slabs, int framed,
+                 fo_agg *a, uint64_t *cms, int depth, int wlog2, int n_threads, fo_batch_result *res)
+{
+    size_t n = 0;
+    for (int i = 0; i < n_slabs; i++) n += ns[i];
     if (n_threads < 1) n_threads = 1;
     if ((size_t)n_threads > n && n > 0) n_threads = (int)n;
     worker_t *ws = (worker_t *)calloc((size_t)n_threads, sizeof(worker_t));
@@ -688,8 +738,10 @@ int fo_run_batch(const uint8_t *buf, const uint32_t *offsets, size_t n, int fram
     double t0 = now_s();
     for (int t = 0; t < n_threads; t++) {
         worker_t *w = &ws[t];
-        w->buf = buf;
+        w->bufs = bufs;
         w->offsets = offsets;
+        w->ns = ns;
+        w->n_slabs = n_slabs;
         w->lo = n * (size_t)t / (size_t)n_threads;
         w->hi = n * (size_t)(t + 1) / (size_t)n_threads;
         w->framed = framed;
@@ -711,18 +763,30 @@ int fo_run_batch(const uint8_t *buf, const uint32_t *offsets, size_t n, int fram
     } else {
         for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, worker_main, &ws[t]);
         for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
-        /* final merge of the per-thread tables */
+        /* final merge of the per-thread tables, itself parallel: merger t
+         * owns the keys with hash % T == t and the sketch columns [t*W/T, (t+1)*W/T) */
+        merge_t *ms = (merge_t *)calloc((size_t)n_threads, sizeof(merge_t));
         for (int t = 0; t < n_threads; t++) {
-            worker_t *w = &ws[t];
-            if (w->agg) {
-                for (size_t i = 0; i < w->agg->cap; i++)
-                    if (w->agg->used[i]) fo_agg_add_row(a, &w->agg->slots[i]);
-                fo_agg_free(w->agg);
+            ms[t].ws = ws;
+            ms[t].n_workers = n_threads;
+            ms[t].me = t;
+            ms[t].out = a ? fo_agg_new(a->key_mode, a->scale) : NULL;
+            ms[t].cms_out = cms;
+            ms[t].cms_words = cms_words;
+            pthread_create(&th[t], NULL, merge_main, &ms[t]);
+        }
+        for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+        for (int t = 0; t < n_threads; t++) {
+            if (ms[t].out) { /* disjoint key sets: plain inserts */
+                for (size_t i = 0; i < ms[t].out->cap; i++)
+                    if (ms[t].out->used[i]) fo_agg_add_row(a, &ms[t].out->slots[i]);
+                fo_agg_free(ms[t].out);
             }
-            if (w->cms) {
-                for (size_t i = 0; i < cms_words; i++) cms[i] += w->cms[i];
-                free(w->cms);
-            }
+        }
+        free(ms);
+        for (int t = 0; t < n_threads; t++) {
+            if (ws[t].agg) fo_agg_free(ws[t].agg);
+            if (ws[t].cms) free(ws[t].cms);
         }
     }
     double t1 = now_s();

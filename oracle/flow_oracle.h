@@ -163,6 +163,10 @@ typedef struct fo_batch_result {
 int fo_run_batch(const uint8_t *buf, const uint32_t *offsets, size_t n, int framed, fo_agg *a,
                  uint64_t *cms, int depth, int wlog2, int n_threads, fo_batch_result *res);
 
+/* Same over several slabs (each < 4 GiB) treated as one record stream. */
+int fo_run_slabs(const uint8_t *const *bufs, const uint32_t *const *offsets, const size_t *ns, int n_slabs, int framed,
+                 fo_agg *a, uint64_t *cms, int depth, int wlog2, int n_threads, fo_batch_result *res);
+
 #ifdef __cplusplus
 }
 #endif

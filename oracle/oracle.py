@@ -78,6 +78,9 @@ def lib():
         L.fo_run_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.POINTER(FoBatchResult)]
         L.fo_run_batch.restype = C.c_int
+        L.fo_run_slabs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.POINTER(FoBatchResult)]
+        L.fo_run_slabs.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -181,6 +184,27 @@ def run_batch(buf, offsets, framed=True, key_mode="flows5m", scale=False, cms=No
             L.fo_agg_rows(tmp_agg, rows.ctypes.data, sz)
         L.fo_agg_free(tmp_agg)
     return rows, cms_arr, {"n_records": res.n_records, "n_bad": res.n_bad, "n_nokey": res.n_nokey, "seconds": res.seconds}
+
+
+def run_slabs(slabs, framed=True, key_mode="aspair", threads=1):
+    """Decode + roll-up several (buf, offsets) slabs as one stream (the CPU baseline leg of bench.py)."""
+    L = lib()
+    mode = KEY_MODES[key_mode] if isinstance(key_mode, str) else int(key_mode)
+    bufs = [np.ascontiguousarray(b, dtype=np.uint8) for b, _ in slabs]
+    offs = [np.ascontiguousarray(o, dtype=np.uint32) for _, o in slabs]
+    k = len(slabs)
+    pb = (C.c_void_p * k)(*[b.ctypes.data for b in bufs])
+    po = (C.c_void_p * k)(*[o.ctypes.data for o in offs])
+    pn = (C.c_size_t * k)(*[len(o) - 1 for o in offs])
+    agg = L.fo_agg_new(mode, 0)
+    res = FoBatchResult()
+    L.fo_run_slabs(pb, po, pn, k, int(framed), agg, None, 0, 0, int(threads), C.byref(res))
+    sz = L.fo_agg_size(agg)
+    rows = np.zeros(sz, dtype=ROW_DTYPE)
+    if sz:
+        L.fo_agg_rows(agg, rows.ctypes.data, sz)
+    L.fo_agg_free(agg)
+    return rows, {"n_records": res.n_records, "n_bad": res.n_bad, "n_nokey": res.n_nokey, "seconds": res.seconds}
 
 
 def topk(cms_arr, depth, wlog2, n_words, cand_rows, k):
