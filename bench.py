@@ -105,6 +105,23 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores():
+    """Host threads this process can really use: the cgroup CPU quota (cpu.max) caps the GPU
+    boxes well below os.cpu_count(), and oversubscribing a throttled cgroup is slower, not faster."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_run(slabs, threads):
     """The CPU restatement (oracle/flow_oracle.c) over host slabs [(bytes, offsets)], all threads."""
     from oracle import oracle as o
@@ -117,7 +134,7 @@ def host_slabs(fp, cfg, first, n_flows, slab):
     from concurrent.futures import ThreadPoolExecutor
 
     jobs = [(first + a, min(slab, n_flows - a)) for a in range(0, n_flows, slab)]
-    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(max_workers=min(len(jobs), usable_cores())) as ex:
         return list(ex.map(lambda j: fp.mocker_host(cfg, j[0], j[1]), jobs))
 
 
@@ -127,8 +144,8 @@ def run_reference(args, rank, world):
         return 0
     import flow_pipeline_b200 as fp
 
-    cores = os.cpu_count() or 1
-    n = min(args.flows, max(1 << 22, min(N_FLOWS, (1 << 20) * cores)))  # bounded sample of the same stream
+    cores = usable_cores()
+    n = min(args.flows, max(1 << 22, min(N_FLOWS, (1 << 21) * cores)))  # bounded sample of the same stream
     cfg = mocker_cfg(fp)
     slabs = host_slabs(fp, cfg, 0, n, 1 << 20)
     times = []
@@ -147,7 +164,7 @@ def run_reference(args, rank, world):
                    "note": "Go inserter + Clickhouse cannot run here (no Go toolchain/DB); this is the C restatement "
                            "oracle/flow_oracle.c, all host threads, per-thread tables merged in parallel at the end"},
         "cpu_baseline": {"value": v, "unit": "flows/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} flows of the same stream per step, {cores} pthreads"},
+                         "sample": f"{n} flows of the same stream per step, {cores} pthreads (cgroup quota; os.cpu_count()={os.cpu_count()})"},
         "e2e": {"value": v, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -292,8 +309,8 @@ def main():
     # ---- CPU baseline on the box's host cores (rank 0, bounded sample) ----
     cpu = None
     if rank == 0 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        n_want = min(n_flows, max(1 << 22, (1 << 20) * cores))
+        cores = usable_cores()
+        n_want = min(n_flows, max(1 << 22, (1 << 21) * cores))
         hs, n_s = [], 0
         for (d_buf, d_off, n, nb) in slabs:  # the same bytes the GPU just processed
             if n_s >= n_want:
@@ -311,7 +328,8 @@ def main():
         assert np.array_equal(chk.flush(), crow), "GPU and CPU roll-ups differ"
         chk.close()
         cpu = {"value": n_s / cres["seconds"], "unit": "flows/s", "cores": cores, "kind": "port",
-               "sample": f"first {n_s} flows of the same stream, {cores} pthreads, per-thread tables merged in parallel",
+               "sample": f"first {n_s} flows of the same stream, {cores} pthreads (cgroup quota; os.cpu_count()={os.cpu_count()}), "
+                         "per-thread tables merged in parallel",
                "single_thread_value": m1 / c1res["seconds"]}
         del hs
 
