@@ -273,10 +273,16 @@ template <uint32_t NEED>
 __device__ __forceinline__ bool varint_field_needed(uint32_t num)
 {
     constexpr uint32_t M0 = need_mask_lo(NEED), M1 = need_mask_hi(NEED);
-    // funnel shift with clamp: a shift of 32 or more yields 0, so out-of-range numbers are "not needed"
-    uint32_t bit = __funnelshift_rc(M0, 0u, num);
-    if (M1 != 0u) bit = num < 32u ? bit : __funnelshift_rc(M1, 0u, num - 32u);
-    return (bit & 1u) != 0u;
+    // shl.b32 clamps: a shift of 32 or more yields 0, so out-of-range numbers are "not needed"
+    uint32_t bit;
+    asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(num));
+    bool need = (bit & M0) != 0u;
+    if (M1 != 0u) {
+        uint32_t bit1;
+        asm("shl.b32 %0, 1, %1;" : "=r"(bit1) : "r"(num - 32u));  // num < 32 wraps to a huge shift: 0
+        need = need || (bit1 & M1) != 0u;
+    }
+    return need;
 }
 
 // everything that is neither a varint nor length-delimited: fixed32/fixed64 skips, group skips,
@@ -303,6 +309,7 @@ __device__ __noinline__ uint32_t skip_other(const Src s, uint32_t pos, uint32_t 
 template <uint32_t NEED, class Src>
 __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const uint32_t end, Flow &f)
 {
+    bool zero_field = false;  // a field number 0 was seen (illegal); checked once, after the loop
     while (pos < end) {
         uint32_t lo, hi;
         s.window(pos, lo, hi);
@@ -334,25 +341,33 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
             pos += t.n;
             s.window(pos, xlo, xhi);  // the window restarts on the value
         }
+        zero_field |= (num == 0u);
         // xlo/xhi: bytes pos.. (at least 6 valid)
         if (__builtin_expect(wt == 0, 1)) {
             // ---- varint ----
             const uint32_t stop = ~xlo & 0x80808080u;  // terminator bytes among the first four
-            if (__builtin_expect(stop == 0u && (xhi & 0x80u) != 0u, 0)) {
+            if (__builtin_expect(stop != 0u, 1)) {
+                // 1..4 bytes
+                const uint32_t t = __ffs(stop);  // 8,16,24,32
+                pos += t >> 3;
+                if (varint_field_needed<NEED>(num)) {
+                    const uint32_t x = xlo & (0xFFFFFFFFu >> ((32u - t) & 31u));
+                    const uint32_t v = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
+                    store_varint_field<NEED>(f, num, (unsigned long long)v);
+                }
+            } else if (!(xhi & 0x80u)) {
+                // 5 bytes: every Unix timestamp since 1978
+                pos += 5u;
+                if (varint_field_needed<NEED>(num)) {
+                    const uint32_t x = xlo;
+                    const uint32_t low28 = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
+                    const uint32_t b4 = xhi & 0x7fu;  // bits 28..34
+                    store_varint_field<NEED>(f, num, ((unsigned long long)(b4 >> 4) << 32) | (unsigned long long)(low28 | (b4 << 28)));
+                }
+            } else {
                 const VarintRes r = varint_slow(s, pos, end);  // six bytes or more
                 pos = r.n ? pos + r.n : FA_POS_ERR;
                 store_varint_field<NEED>(f, num, r.v);
-            } else {
-                const uint32_t t = __ffs(stop);  // 8,16,24,32, or 0: five bytes
-                pos += stop ? (t >> 3) : 5u;
-                if (varint_field_needed<NEED>(num)) {
-                    const uint32_t keep = stop ? (0xFFFFFFFFu >> ((32u - t) & 31u)) : 0xFFFFFFFFu;
-                    const uint32_t x = xlo & keep;
-                    const uint32_t low28 = (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
-                    const uint32_t b4 = stop ? 0u : (xhi & 0x7fu);  // fifth byte: bits 28..34
-                    const unsigned long long v = ((unsigned long long)(b4 >> 4) << 32) | (unsigned long long)(low28 | (b4 << 28));
-                    store_varint_field<NEED>(f, num, v);
-                }
             }
         } else if (wt == 2) {
             // ---- length-delimited ----
@@ -388,9 +403,10 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
         } else {
             pos = skip_other(s, pos, end, wt, num);  // FA_POS_ERR on error
         }
-        if (num == 0u) pos = FA_POS_ERR;  // field number 0 is illegal
     }
-    return pos == end;  // anything that ran past the end of the record is an error too
+    // good iff the loop ended exactly on `end` (anything that ran past the record is an error)
+    // and no field carried the illegal number 0
+    return pos == end && !zero_field;
 }
 
 // Decode the record occupying [pos,end): bare message, or varint(len) || message
