@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -289,18 +290,27 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 // kernel launch
 // ---------------------------------------------------------------------------------------------
 
-template <class Consumer>
-static cudaError_t launch_tile(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
+template <class Consumer, int THREADS>
+static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
     const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;
     static thread_local size_t configured = 0;  // per kernel instantiation and host thread
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
+        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
         if (e != cudaSuccess) return e;
         configured = kTileBytesMax + kTilePad + 16;
     }
-    k_tile<Consumer><<<n_tiles, kThreads, smem, c->stream>>>(tp);
+    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
     return cudaGetLastError();
+}
+
+template <class Consumer>
+static cudaError_t launch_tile(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
+{
+    if (tp.p.tile_records <= 128) return launch_tile_t<Consumer, 128>(c, tp, n_tiles);
+    if (tp.p.tile_records <= 256) return launch_tile_t<Consumer, 256>(c, tp, n_tiles);
+    if (tp.p.tile_records <= 512) return launch_tile_t<Consumer, 512>(c, tp, n_tiles);
+    return launch_tile_t<Consumer, 1024>(c, tp, n_tiles);
 }
 
 template <int MODE>
@@ -350,7 +360,8 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
     // the shared-memory budget, fewer for fat records
     const double avg = (double)len / (double)n_records;
-    uint32_t tr = kThreads;
+    static const uint32_t max_tile = getenv("FA_TILE_RECORDS") ? (uint32_t)atoi(getenv("FA_TILE_RECORDS")) : (uint32_t)kThreads;
+    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~31u, 32u), 1024u);
     while (tr > 32 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 32;
     uint32_t tb = (uint32_t)((double)tr * avg * 1.06 + 512.0);
     tb = (tb + 1023u) & ~1023u;

@@ -27,7 +27,7 @@ namespace fa {
 
 constexpr int kThreads = 256;            // one record per thread per tile
 constexpr int kTilePad = 64;             // over-read slack behind the tile (then the mbarrier)
-constexpr int kTileBytesMax = 96 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 24 KB)
+constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 24 KB)
 
 struct Counters {
     unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows;
@@ -499,8 +499,8 @@ __device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad
 
 // ---- the tile kernel: decode (+ consume) one tile per CTA ------------------------------------
 
-template <class Consumer>
-__global__ void __launch_bounds__(kThreads, Consumer::MIN_BLOCKS) k_tile(const __grid_constant__ TileParams tp)
+template <class Consumer, int THREADS>
+__global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / THREADS) k_tile(const __grid_constant__ TileParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const SubmitParams &p = tp.p;
