@@ -267,6 +267,9 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     }
     FA_CUDA(c, cudaMalloc(&c->d_counters, sizeof(Counters)));
     FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    // nothing is known about the keys yet: the first submit combines per tile (at worst ~25 % slower than
+    // it had to be; not combining hot keys would be several times slower)
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
         FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
@@ -293,14 +296,18 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 template <class Consumer, int THREADS>
 static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
-    const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;
+    // tile buffer + over-read pad + mbarrier + counter; the buffer doubles as the per-tile combine table,
+    // so it is at least that large (a larger tile_bytes only lets more bytes be staged)
+    TileParams tpl = tp;
+    tpl.p.tile_bytes = std::max<uint32_t>(tp.p.tile_bytes, (Consumer::SMEM_MIN + 15u) & ~15u);
+    const size_t smem = (size_t)tpl.p.tile_bytes + kTilePad + 16;
     static thread_local size_t configured = 0;  // per kernel instantiation and host thread
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
         if (e != cudaSuccess) return e;
         configured = kTileBytesMax + kTilePad + 16;
     }
-    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
+    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tpl);
     return cudaGetLastError();
 }
 
@@ -357,6 +364,8 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.cms_depth = c->cfg.cms_depth;
     p.cms_wlog2 = c->cfg.cms_width_log2;
     p.counters = c->d_counters;
+    p.hint_set = (uint32_t)(c->n_submits & 1u);
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[p.hint_set][0], 0, 8, c->stream));  // this submit's statistics start at zero
     // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
     // the shared-memory budget, fewer for fat records
     const double avg = (double)len / (double)n_records;
@@ -724,6 +733,7 @@ extern "C" int fa_reset(fa_ctx *c)
     if (rc) return rc;
     if (c->d_cms) FA_CUDA(c, cudaMemsetAsync(c->d_cms, 0, c->cms_words * 8, c->stream));
     FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     c->n_records = c->n_submits = c->bytes_in = 0;
     return fa_sync(c);
 }

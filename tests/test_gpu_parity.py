@@ -383,3 +383,22 @@ def test_host_inserter_mirror_rows_equal_oracle(fp, oracle, torch_cuda, tmp_path
             ts = time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(w["key"][0])))
             want.append((str(w["key"][1]), str(w["key"][2]), f"[{w['key'][3]}]", str(w["bytes"]), str(w["packets"]), str(w["count"]), ts))
     assert got == sorted(want)
+
+
+@pytest.mark.parametrize("mode,addr_mode,cms", [("flows5m", 0, False), ("aspair", 0, False), ("srcaddr", 1, True), ("dstport", 0, False)])
+def test_hot_keys_take_the_per_tile_combine_path(fp, oracle, torch_cuda, mode, addr_mode, cms):
+    """Skewed keys (the mocker's own 9 AS pairs; Zipf addresses): from the second submit on a context
+    combines each tile in shared memory before touching the table.  Same rows, same sketch."""
+    cfg = fp.FaMockerConfig.make(seed=31, flows_per_second=300, addr_mode=addr_mode, framed=True)
+    n = 120_000
+    buf, offs = fp.mocker_host(cfg, 0, n)
+    want, wcms, res = oracle.run_batch(buf, offs, key_mode=mode, cms=(4, 12) if cms else None)
+    with fp.FlowAgg(mode, cms=cms, cms_depth=4, cms_width_log2=12, table_capacity=1 << 18) as a:
+        third = n // 3
+        for lo, hi in ((0, third), (third, 2 * third), (2 * third, n)):   # three submits: direct, then combined
+            a.submit(buf[offs[lo]:offs[hi]], (offs[lo:hi + 1] - offs[lo]).astype(np.uint32))
+        st = a.stats()
+        assert st["n_records"] == n and st["n_bad"] == 0
+        if cms:
+            assert np.array_equal(a.cms_read(), wcms)
+        assert np.array_equal(a.flush(), want)
