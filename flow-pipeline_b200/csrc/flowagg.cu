@@ -46,6 +46,8 @@ struct fa_ctx {
     int num_sms = 148;
 
     uint8_t *d_slots = nullptr;
+    uint8_t *d_hot = nullptr;  // hot-key replicas (key modes with KW <= 4)
+    bool hot_dirty = false;    // replicas may hold sums not yet folded into d_slots
     unsigned long long *d_cms = nullptr, *d_cms_global = nullptr;
     size_t cms_words = 0;
     Counters *d_counters = nullptr;
@@ -131,7 +133,41 @@ static cudaError_t launch_table_init(fa_ctx *c)
     const unsigned long long words = n_slots * (SlotLayout<KW>::BYTES / 8);
     const int grid = (int)std::min<unsigned long long>((words + 255) / 256, (unsigned long long)c->num_sms * 32);
     k_table_init<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots);
+    if (c->d_hot) k_table_init<KW><<<c->num_sms, 256, 0, c->stream>>>(c->d_hot, (unsigned long long)kHotReplicas * kHotSlots);
+    c->hot_dirty = false;
     return cudaGetLastError();
+}
+
+static void fill_table_params(fa_ctx *c, SubmitParams &p)
+{
+    p.slots = c->d_slots;
+    p.slot_mask = (uint32_t)(c->capacity - 1);
+    p.counters = c->d_counters;
+    p.hot_slots = c->d_hot;
+}
+
+template <int KW>
+static cudaError_t launch_merge_hot(fa_ctx *c)
+{
+    SubmitParams p{};
+    fill_table_params(c, p);
+    k_merge_hot<KW><<<c->num_sms, 256, 0, c->stream>>>(p, kHotReplicas * kHotSlots);
+    return cudaGetLastError();
+}
+
+// fold the hot-key replicas into the main table (before anything reads it)
+static int merge_hot(fa_ctx *c)
+{
+    if (!c->d_hot || !c->hot_dirty) return FA_OK;
+    cudaError_t e;
+    switch (c->kw) {
+    case 1: e = launch_merge_hot<1>(c); break;
+    case 2: e = launch_merge_hot<2>(c); break;
+    default: e = launch_merge_hot<4>(c); break;
+    }
+    FA_CUDA(c, e);
+    c->hot_dirty = false;
+    return FA_OK;
 }
 
 // empty table: all-ones keys (CAS layouts) / state 0 (wide keys), zero sums
@@ -156,6 +192,7 @@ extern "C" void fa_destroy(fa_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_slots);
+    cudaFree(c->d_hot);
     cudaFree(c->d_cms);
     cudaFree(c->d_cms_global);
     cudaFree(c->d_counters);
@@ -273,6 +310,7 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
         FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
+        if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * kHotSlots * c->slot_bytes));
         int rc = table_init(c);
         if (rc) return rc;
     }
@@ -296,18 +334,14 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 template <class Consumer, int THREADS>
 static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
-    // tile buffer + over-read pad + mbarrier + counter; the buffer doubles as the per-tile combine table,
-    // so it is at least that large (a larger tile_bytes only lets more bytes be staged)
-    TileParams tpl = tp;
-    tpl.p.tile_bytes = std::max<uint32_t>(tp.p.tile_bytes, (Consumer::SMEM_MIN + 15u) & ~15u);
-    const size_t smem = (size_t)tpl.p.tile_bytes + kTilePad + 16;
+    const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;  // tile buffer + over-read pad + mbarrier
     static thread_local size_t configured = 0;  // per kernel instantiation and host thread
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
         if (e != cudaSuccess) return e;
         configured = kTileBytesMax + kTilePad + 16;
     }
-    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tpl);
+    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
     return cudaGetLastError();
 }
 
@@ -357,14 +391,13 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.offsets = d_offsets;
     p.n_records = n_records;
     p.framed = (flags & FA_FRAMED) ? 1u : 0u;
-    p.slots = c->d_slots;
-    p.slot_mask = (uint32_t)(c->capacity - 1);
+    fill_table_params(c, p);
     p.scale = (c->cfg.flags & FA_CFG_SCALE_SAMPLING) ? 1u : 0u;
     p.cms = c->d_cms;
     p.cms_depth = c->cfg.cms_depth;
     p.cms_wlog2 = c->cfg.cms_width_log2;
-    p.counters = c->d_counters;
     p.hint_set = (uint32_t)(c->n_submits & 1u);
+    if (c->d_hot) c->hot_dirty = true;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[p.hint_set][0], 0, 8, c->stream));  // this submit's statistics start at zero
     // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
     // the shared-memory budget, fewer for fat records
@@ -559,6 +592,8 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
     if (!c || !out) return FA_ERR_INVALID;
     int rc = fa_sync(c);
     if (rc) return rc;
+    rc = merge_hot(c);
+    if (rc) return rc;
     rc = read_counters(c);
     if (rc) return rc;
     out->n_records = c->n_records;
@@ -672,6 +707,8 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
 {
     if (!c || !n || !c->d_slots) return FA_ERR_INVALID;
     int rc = fa_sync(c);
+    if (rc) return rc;
+    rc = merge_hot(c);
     if (rc) return rc;
     rc = read_counters(c);
     if (rc) return rc;
@@ -793,6 +830,8 @@ extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t 
 {
     if (!c || !n || !c->d_cms || !c->d_slots || (k && !out)) return FA_ERR_INVALID;
     int rc = fa_sync(c);
+    if (rc) return rc;
+    rc = merge_hot(c);
     if (rc) return rc;
     rc = read_counters(c);
     if (rc) return rc;

@@ -29,6 +29,10 @@ constexpr int kThreads = 256;            // one record per thread per tile
 constexpr int kTilePad = 64;             // over-read slack behind the tile (then the mbarrier)
 constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 24 KB)
 
+constexpr uint32_t kHotReplicas = 64;  // CTA b uses replica b mod 64
+constexpr uint32_t kHotSlots = 1024;   // slots per replica (power of two)
+constexpr uint32_t kHotProbes = 8;     // bounded probe sequence; a miss falls through to the main table
+
 struct Counters {
     unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows;
     unsigned int side_state, pad0;
@@ -55,6 +59,8 @@ struct SubmitParams {
     uint32_t cms_depth, cms_wlog2;
     Counters *counters;
     uint32_t hint_set;  // this submit writes counters->hint[hint_set], reads hint[hint_set ^ 1]
+    // hot-key replicas: kHotReplicas small tables of kHotSlots slots (same slot layout as the main table)
+    uint8_t *hot_slots;
 };
 
 // ---- key modes ----------------------------------------------------------------------
@@ -288,6 +294,57 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
     atomicAdd(&p.counters->n_dropped, count);
 }
 
+// Bounded insert into one hot-key replica (KW <= 4 layouts only).  Returns false when the probe
+// sequence is exhausted (replica full of other keys): the caller then uses the main table.
+// Does not count groups: replicas are folded into the main table before anything reads it.
+template <int KW>
+__device__ __forceinline__ bool hot_add(uint8_t *replica, const uint32_t *key, unsigned long long h, unsigned long long bytes,
+                                        unsigned long long packets)
+{
+    uint32_t slot = (uint32_t)(h >> 20) & (kHotSlots - 1u);
+    if (KW <= 2) {
+        const unsigned long long k = (unsigned long long)key[0] | (KW == 2 ? (unsigned long long)key[1] << 32 : 0ull);
+        if (k == ~0ull) return false;
+#pragma unroll 1
+        for (uint32_t probe = 0; probe < kHotProbes; probe++) {
+            uint8_t *s = replica + (size_t)slot * SlotLayout<KW>::BYTES;
+            unsigned long long cur = ld_relaxed_u64(s);
+            if (cur == ~0ull) {
+                cur = atomicCAS(reinterpret_cast<unsigned long long *>(s), ~0ull, k);
+                if (cur == ~0ull) cur = k;
+            }
+            if (cur == k) {
+                slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, 1ull);
+                return true;
+            }
+            slot = (slot + 1) & (kHotSlots - 1u);
+        }
+    } else {
+        const unsigned long long klo = (unsigned long long)key[0] | ((unsigned long long)key[1] << 32);
+        const unsigned long long khi = (unsigned long long)key[2] | ((unsigned long long)key[3] << 32);
+        if ((klo & khi) == ~0ull) return false;
+#pragma unroll 1
+        for (uint32_t probe = 0; probe < kHotProbes; probe++) {
+            uint8_t *s = replica + (size_t)slot * SlotLayout<KW>::BYTES;
+            unsigned long long clo, chi;
+            ld_relaxed_u128(s, clo, chi);
+            if ((clo & chi) == ~0ull) {
+                cas_u128(s, ~0ull, ~0ull, klo, khi, clo, chi);
+                if ((clo & chi) == ~0ull) {
+                    clo = klo;
+                    chi = khi;
+                }
+            }
+            if (clo == klo && chi == khi) {
+                slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, 1ull);
+                return true;
+            }
+            slot = (slot + 1) & (kHotSlots - 1u);
+        }
+    }
+    return false;
+}
+
 // count-min sketch update: idx_j = (lo32(h) + j*(hi32(h)|1)) mod w
 __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long long h, unsigned long long weight)
 {
@@ -299,14 +356,18 @@ __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long lon
     }
 }
 
+// One decoded flow into the group table (+ sketch).  hot: this submit sends updates through the CTA's
+// replica first (keys repeat a lot: one shared slot per key would serialise in L2).
+// Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
 template <int MODE>
-__device__ __forceinline__ void aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey)
+__device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have)
 {
     constexpr int KW = KeyTraits<MODE>::KW;
     uint32_t key[KW];
-    if (!make_key<MODE>(f, key)) {
+    have = make_key<MODE>(f, key);
+    if (!have) {
         nokey++;
-        return;
+        return 0u;
     }
     const unsigned long long h = hash64<KW>(key);
     unsigned long long b = f.bytes, pk = f.packets;
@@ -314,8 +375,14 @@ __device__ __forceinline__ void aggregate_flow(const SubmitParams &p, const Flow
         b *= f.sampling_rate;
         pk *= f.sampling_rate;
     }
-    if (p.slots) table_add<KW>(p, key, h, b, pk, 1ull);
+    if (p.slots) {
+        bool done = false;
+        if (KW <= 4 && hot)
+            done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, h, b, pk);
+        if (!done) table_add<KW>(p, key, h, b, pk, 1ull);
+    }
     if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
+    return (uint32_t)h;
 }
 
 // ---- tile staging: one bulk-async copy per tile ----------------------------------------------
@@ -408,192 +475,56 @@ struct TileParams {
     Columns c;  // only read by ColConsumer
 };
 
-// ---- per-tile pre-aggregation for hot keys ---------------------------------------------------------
+// ---- hot keys --------------------------------------------------------------------------------------
 //
 // Real flow data is skewed (the reference's own mocker draws from 9 AS pairs, mocker.go:61-62): with one
-// global reduction per record the hottest slots serialise in L2 (measured: 3.5 G flows/s on 18 groups against
-// 23 G on 65 536).  When a tile's keys repeat, its records are first combined in a shared-memory table that
-// reuses the tile buffer (dead once every record is parsed), then each distinct key costs ONE global update
-// per tile, and one sketch update (the sketch is linear).  Tiles whose keys do not repeat skip all of it.
-constexpr uint32_t kCombineSlots = 512;  // > 256 records per tile: the probe always terminates
-
-template <int KW>
-__host__ __device__ constexpr uint32_t combine_bytes()
-{
-    // tags u64 | bytes u64 | packets u64 | weight u64 | count u32 | keys u32[KW]
-    return kCombineSlots * (8u + 8u + 8u + 8u + 4u + 4u * KW);
-}
-
-// shared-memory 64-bit add as two native 32-bit atomics (the carry is this thread's own wrap)
-__device__ __forceinline__ void smem_add_u64(uint32_t addr, unsigned long long v)
-{
-    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(lo) : "memory");
-    const uint32_t carry = (old + lo) < old ? 1u : 0u;
-    if (hi + carry) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr + 4u), "r"(hi + carry) : "memory");
-}
-
+// shared slot per key the hottest slots serialise in L2 (measured: 3.5 G flows/s on 18 groups against 23 G
+// on 65 536).  Every submit samples how often keys repeat inside a warp (every 64th tile); when the previous
+// submit of the context saw >= 1/16 of its lanes repeating, CTAs send their updates to one of 64 small replica
+// tables (same fire-and-forget reductions, 64x less contention per address); replicas are folded into the main
+// table before anything reads it.  The very first submit of a context assumes hot keys.
 template <int MODE, bool WEIGHTED>
 struct AggConsumer {
     static constexpr int KW = KeyTraits<MODE>::KW;
     static constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
     static constexpr int MIN_BLOCKS = KW <= 4 ? 8 : 5;  // 32 / 48 registers per thread
-    static constexpr bool COMBINE = KW <= 4;             // 5-tuples are high-cardinality by nature: always direct
-    static constexpr uint32_t SMEM_MIN = COMBINE ? combine_bytes<KW <= 4 ? KW : 1>() : 0u;
-
-    // what one record contributes; nothing is written to global memory yet
+    static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     struct Item {
+        uint32_t h32;
         bool have;
-        uint32_t key[KW];
-        unsigned long long h, bytes, packets, weight;
     };
-
-    static __device__ __forceinline__ void prepare(const TileParams &tp, bool ok, Flow &f, Item &it, uint32_t &bad, uint32_t &nokey)
+    static __device__ __forceinline__ void item_clear(Item &it)
     {
+        it.h32 = 0;
         it.have = false;
-        if (!ok) {
-            bad++;  // inserter.go:125-126: log, skip the row
-            return;
-        }
-        if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-        if (!make_key<MODE>(f, it.key)) {
-            nokey++;
-            return;
-        }
-        it.have = true;
-        it.h = hash64<KW>(it.key);
-        it.bytes = f.bytes;
-        it.packets = f.packets;
-        if (tp.p.scale) {  // sum(Bytes*SamplingRate): viz-ch.json:74
-            it.bytes *= f.sampling_rate;
-            it.packets *= f.sampling_rate;
-        }
-        if (WEIGHTED) it.weight = f.bytes * f.sampling_rate;  // viz-ch.json:233 heavy-hitter weight (else: Bytes)
     }
-
-    static __device__ __forceinline__ void update_direct(const SubmitParams &p, const Item &it)
+    static __device__ __forceinline__ bool want_hot(const SubmitParams &p)
     {
-        if (!it.have) return;
-        if (p.slots) table_add<KW>(p, it.key, it.h, it.bytes, it.packets, 1ull);
-        if (WEIGHTED && p.cms) cms_add(p, it.h, it.weight);  // FA_CFG_CMS implies the WEIGHTED instantiation
+        if (!HOT || !p.hot_slots) return false;
+        const unsigned int d = __ldg(&p.counters->hint[p.hint_set ^ 1u][0]), n = __ldg(&p.counters->hint[p.hint_set ^ 1u][1]);
+        return n != 0u && d * 16u >= n;  // >= 1/16 of the sampled lanes repeat
     }
-
-    static __device__ __forceinline__ void item_clear(Item &it) { it.have = false; }
-    static __device__ __forceinline__ void item_from_scalars(Item &it, bool have, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3,
-                                                             unsigned long long h, unsigned long long b, unsigned long long pk,
-                                                             unsigned long long w)
-    {
-        const uint32_t k[4] = {k0, k1, k2, k3};
-        it.have = have;
-#pragma unroll
-        for (int i = 0; i < KW && i < 4; i++) it.key[i] = k[i];
-        it.h = h;
-        it.bytes = b;
-        it.packets = pk;
-        it.weight = w;
-    }
-    static __device__ __forceinline__ void call_staged(const TileParams &tp, const Item &it, uint8_t *smem, bool combine);
-
-    // decode result straight into the table: the path of every tile whose keys do not repeat, and of
-    // the out-of-line global-memory records
-    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey)
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
+                                                   Item &it)
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            aggregate_flow<MODE>(tp.p, f, nokey);
+            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
     }
-
-    // Should this submit combine records per tile before touching the table?  Decided from the key
-    // repetition the previous submit of this context observed: >= 1/4 of the sampled lanes shared
-    // their key with a neighbour in the warp.
-    static __device__ __forceinline__ bool want_combine(const SubmitParams &p)
-    {
-        if (!COMBINE) return false;
-        const unsigned int d = __ldg(&p.counters->hint[p.hint_set ^ 1u][0]), n = __ldg(&p.counters->hint[p.hint_set ^ 1u][1]);
-        return n != 0u && d * 4u >= n;
-    }
-
     // every 64th tile measures how often keys repeat inside a warp (feeds the next submit's decision)
-    static __device__ __forceinline__ bool is_sampled() { return COMBINE && (blockIdx.x & 63u) == 0u; }
     static __device__ __forceinline__ void sample_repeats(const SubmitParams &p, const Item &it)
     {
-        const uint32_t h32 = it.have ? (uint32_t)it.h : (0x9E3779B9u * (threadIdx.x + 1u));
+        if (!HOT || (blockIdx.x & 63u) != 0u) return;
+        const uint32_t h32 = it.have ? it.h32 : (0x9E3779B9u * (threadIdx.x + 1u));
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h32);
         const uint32_t dups = __popc(__ballot_sync(0xFFFFFFFFu, it.have && __popc(peers) > 1));
         const uint32_t lanes = __popc(__ballot_sync(0xFFFFFFFFu, it.have));
         if ((threadIdx.x & 31) == 0 && lanes) {
             atomicAdd(&p.counters->hint[p.hint_set][0], dups);
             atomicAdd(&p.counters->hint[p.hint_set][1], lanes);
-        }
-    }
-
-    // Tile epilogue in combine mode, executed by every thread of the CTA.  smem: the tile buffer (all
-    // parsing is done after the first barrier).
-    static __device__ __forceinline__ void combine_tile(const TileParams &tp, const Item &it, uint8_t *smem)
-    {
-        const SubmitParams &p = tp.p;
-        __syncthreads();  // every thread has finished reading the tile bytes
-
-        // ---- combine in shared memory ----
-        constexpr uint32_t S = kCombineSlots;
-        const uint32_t base = smem_u32(smem);
-        const uint32_t tags = base, sb = base + S * 8u, sp = base + S * 16u, sw = base + S * 24u, sc = base + S * 32u, sk = base + S * 36u;
-        for (uint32_t i = threadIdx.x; i < S * 36u / 16u; i += blockDim.x)  // tags, sums and counts to zero
-            asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(base + i * 16u), "r"(0u) : "memory");
-        __syncthreads();
-        uint32_t slot = 0;
-        if (it.have) {  // claim or find the slot of this key's hash (the tag); the claimer writes the key
-            const unsigned long long tag = it.h | 1ull;
-            slot = (uint32_t)(it.h >> 40) & (S - 1u);
-            for (;;) {
-                unsigned long long cur;
-                asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(cur) : "r"(tags + slot * 8u), "l"(0ull), "l"(tag) : "memory");
-                if (cur == 0ull) {
-#pragma unroll
-                    for (int k = 0; k < KW; k++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sk + (slot * KW + k) * 4u), "r"(it.key[k]) : "memory");
-                    break;
-                }
-                if (cur == tag) break;
-                slot = (slot + 1u) & (S - 1u);
-            }
-        }
-        __syncthreads();  // keys are published
-        if (it.have) {
-            bool same = true;  // equal tags almost surely mean equal keys; verify, never assume
-#pragma unroll
-            for (int k = 0; k < KW; k++) {
-                uint32_t w;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sk + (slot * KW + k) * 4u) : "memory");
-                same &= (w == it.key[k]);
-            }
-            if (same) {
-                smem_add_u64(sb + slot * 8u, it.bytes);
-                smem_add_u64(sp + slot * 8u, it.packets);
-                if (WEIGHTED && p.cms) smem_add_u64(sw + slot * 8u, it.weight);
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sc + slot * 4u), "r"(1u) : "memory");
-            } else {
-                update_direct(p, it);  // a genuine 64-bit hash collision inside one tile
-            }
-        }
-        __syncthreads();  // sums are complete
-        for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
-            uint32_t cnt;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cnt) : "r"(sc + s * 4u) : "memory");
-            if (!cnt) continue;
-            uint32_t key[KW];
-#pragma unroll
-            for (int k = 0; k < KW; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(key[k]) : "r"(sk + (s * KW + k) * 4u) : "memory");
-            unsigned long long b, pk, w;
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(b) : "r"(sb + s * 8u) : "memory");
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(pk) : "r"(sp + s * 8u) : "memory");
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(w) : "r"(sw + s * 8u) : "memory");
-            const unsigned long long h = hash64<KW>(key);
-            if (p.slots) table_add<KW>(p, key, h, b, pk, (unsigned long long)cnt);
-            if (p.cms) cms_add(p, h, w);
         }
     }
 };
@@ -608,21 +539,14 @@ __device__ __forceinline__ uint4 addr_bytes(const uint32_t be[4])
 struct ColConsumer {
     static constexpr uint32_t NEED = F_ALL;
     static constexpr int MIN_BLOCKS = 4;  // all 16 fields live: 64 registers per thread
-    static constexpr uint32_t SMEM_MIN = 0;
     struct Item {};
-    static __device__ __forceinline__ void prepare(const TileParams &tp, uint32_t r, bool ok, Flow &f, Item &, uint32_t &bad, uint32_t &nokey)
+    static __device__ __forceinline__ void item_clear(Item &) {}
+    static __device__ __forceinline__ bool want_hot(const SubmitParams &) { return false; }
+    static __device__ __forceinline__ void sample_repeats(const SubmitParams &, const Item &) {}
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool, Item &)
     {
         consume(tp, r, ok, f, bad, nokey);
     }
-    static __device__ __forceinline__ bool want_combine(const SubmitParams &) { return false; }
-    static __device__ __forceinline__ bool is_sampled() { return false; }
-    static __device__ __forceinline__ void sample_repeats(const SubmitParams &, const Item &) {}
-    static __device__ __forceinline__ void update_direct(const SubmitParams &, const Item &) {}
-    static __device__ __forceinline__ void combine_tile(const TileParams &, const Item &, uint8_t *) {}
-    static __device__ __forceinline__ void item_clear(Item &) {}
-    static __device__ __forceinline__ void item_from_scalars(Item &, bool, uint32_t, uint32_t, uint32_t, uint32_t, unsigned long long,
-                                                             unsigned long long, unsigned long long, unsigned long long) {}
-    static __device__ __forceinline__ void call_staged(const TileParams &, const Item &, uint8_t *, bool) {}
     static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &)
     {
         const Columns &c = tp.c;
@@ -676,7 +600,9 @@ __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32
         s.limit_word = (uint32_t)(((p.len + 15ull) & ~15ull) / 4ull) - 1u;
         ok = decode_record<Consumer::NEED>(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, f);
     }
-    Consumer::consume(tp, r, ok, f, bad, nokey);
+    typename Consumer::Item it;
+    Consumer::item_clear(it);
+    Consumer::consume(tp, r, ok, f, bad, nokey, false, it);
     return bad | (nokey << 1);
 }
 
@@ -690,48 +616,6 @@ __device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad
     }
 }
 
-template <class Consumer>
-__device__ __forceinline__ void consume_or_prepare(const TileParams &tp, uint32_t r, bool ok, Flow &f, typename Consumer::Item &item,
-                                                   uint32_t &bad, uint32_t &nokey);
-template <>
-__device__ __forceinline__ void consume_or_prepare<ColConsumer>(const TileParams &tp, uint32_t r, bool ok, Flow &f, ColConsumer::Item &item,
-                                                                uint32_t &bad, uint32_t &nokey)
-{
-    ColConsumer::prepare(tp, r, ok, f, item, bad, nokey);
-}
-template <class Consumer>
-__device__ __forceinline__ void consume_or_prepare(const TileParams &tp, uint32_t, bool ok, Flow &f, typename Consumer::Item &item,
-                                                   uint32_t &bad, uint32_t &nokey)
-{
-    Consumer::prepare(tp, ok, f, item, bad, nokey);
-}
-
-// Sampling and per-tile combining, out of line so that the common path keeps its registers; the
-// record's contribution travels in scalar arguments (registers), not as a struct (stack).
-// Called by every thread of the CTA (it contains barriers).
-template <class Consumer>
-__device__ __noinline__ void staged_tile_epilogue(const TileParams &tp, uint8_t *smem, bool combine, bool have, uint32_t k0, uint32_t k1,
-                                                  uint32_t k2, uint32_t k3, unsigned long long h, unsigned long long bytes,
-                                                  unsigned long long packets, unsigned long long weight)
-{
-    typename Consumer::Item item;
-    Consumer::item_from_scalars(item, have, k0, k1, k2, k3, h, bytes, packets, weight);
-    Consumer::sample_repeats(tp.p, item);
-    if (combine) Consumer::combine_tile(tp, item, smem);
-    else Consumer::update_direct(tp.p, item);
-}
-
-template <int MODE, bool WEIGHTED>
-__device__ __forceinline__ void AggConsumer<MODE, WEIGHTED>::call_staged(const TileParams &tp, const Item &it, uint8_t *smem, bool combine)
-{
-    if (COMBINE)
-        staged_tile_epilogue<AggConsumer<MODE, WEIGHTED>>(tp, smem, combine, it.have, it.key[0], KW > 1 ? it.key[KW > 1 ? 1 : 0] : 0u,
-                                                          KW > 2 ? it.key[KW > 2 ? 2 : 0] : 0u, KW > 3 ? it.key[KW > 3 ? 3 : 0] : 0u, it.h,
-                                                          it.bytes, it.packets, WEIGHTED ? it.weight : it.bytes);
-    else
-        update_direct(tp.p, it);
-}
-
 // ---- the tile kernel: decode (+ consume) one tile per CTA ------------------------------------
 
 template <class Consumer, int THREADS>
@@ -740,8 +624,7 @@ __global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / T
     extern __shared__ __align__(128) uint8_t smem[];
     const SubmitParams &p = tp.p;
     const TileInfo t = stage_tile(p, blockIdx.x, smem);
-    const bool combine = Consumer::want_combine(p);  // uniform over the grid; the load overlaps the tile copy
-    const bool staged_epilogue = combine || Consumer::is_sampled();  // uniform over the CTA
+    const bool hot = Consumer::want_hot(p);  // uniform over the grid; the load overlaps the tile copy
     uint32_t bad = 0, nokey = 0;
     const bool active = threadIdx.x < t.n;
     const uint32_t r = t.r0 + threadIdx.x;
@@ -760,15 +643,14 @@ __global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / T
             SmemSrc s;
             s.base = smem_u32(smem);
             const bool ok = decode_record<Consumer::NEED>(s, o0 - t.a0, o1 - t.a0, p.framed != 0, f);
-            consume_or_prepare<Consumer>(tp, r, ok, f, item, bad, nokey);
+            Consumer::consume(tp, r, ok, f, bad, nokey, hot, item);
         } else {
             const uint32_t res = record_from_global<Consumer>(tp, r, o0, o1);  // updates the table itself
             bad += res & 1u;
             nokey += res >> 1;
         }
     }
-    if (!staged_epilogue) Consumer::update_direct(p, item);  // the common case: straight into the table
-    else Consumer::call_staged(tp, item, smem, combine);
+    Consumer::sample_repeats(p, item);
     flush_counts(p, bad, nokey);
 }
 
@@ -805,7 +687,8 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
             f.dst[2] = __byte_perm(a.z, 0, 0x0123); f.dst[3] = __byte_perm(a.w, 0, 0x0123);
             f.dst_len = c.dst_addr_len[r] == 255 ? 17u : c.dst_addr_len[r];
         }
-        aggregate_flow<MODE>(p, f, nokey);
+        bool have;
+        aggregate_flow<MODE>(p, f, nokey, false, have);
     }
     flush_counts(p, 0, nokey);
 }
@@ -822,6 +705,34 @@ __global__ void __launch_bounds__(256) k_table_init(uint8_t *slots, unsigned lon
     const unsigned long long total = n_slots * WORDS;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x)
         w[i] = (i % WORDS) < KEY_WORDS64 ? ~0ull : 0ull;
+}
+
+// Fold the hot-key replicas into the main table and empty them (KW <= 4 layouts).
+template <int KW>
+__global__ void __launch_bounds__(256) k_merge_hot(const SubmitParams p, uint32_t n_hot_slots)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hot_slots; i += gridDim.x * blockDim.x) {
+        uint8_t *s = p.hot_slots + (size_t)i * SlotLayout<KW>::BYTES;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(s);
+        uint32_t key[KW];
+        constexpr int KEY64 = KW <= 2 ? 1 : 2;
+        bool empty = true;
+#pragma unroll
+        for (int k = 0; k < KEY64; k++) empty &= (w[k] == ~0ull);
+        if (empty) continue;
+        key[0] = (uint32_t)w[0];
+        if (KW >= 2) key[KW >= 2 ? 1 : 0] = (uint32_t)(w[0] >> 32);
+        if (KW == 4) {
+            key[KW == 4 ? 2 : 0] = (uint32_t)w[KEY64 - 1];
+            key[KW == 4 ? 3 : 0] = (uint32_t)(w[KEY64 - 1] >> 32);
+        }
+        const unsigned long long *v = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
+        table_add<KW>(p, key, hash64<KW>(key), v[0], v[1], v[2]);
+#pragma unroll
+        for (int k = 0; k < KEY64; k++) w[k] = ~0ull;
+        unsigned long long *vv = reinterpret_cast<unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
+        vv[0] = vv[1] = vv[2] = 0ull;
+    }
 }
 
 template <int KW>

@@ -386,9 +386,10 @@ def test_host_inserter_mirror_rows_equal_oracle(fp, oracle, torch_cuda, tmp_path
 
 
 @pytest.mark.parametrize("mode,addr_mode,cms", [("flows5m", 0, False), ("aspair", 0, False), ("srcaddr", 1, True), ("dstport", 0, False)])
-def test_hot_keys_take_the_per_tile_combine_path(fp, oracle, torch_cuda, mode, addr_mode, cms):
+def test_hot_keys_take_the_replica_path(fp, oracle, torch_cuda, mode, addr_mode, cms):
     """Skewed keys (the mocker's own 9 AS pairs; Zipf addresses): from the second submit on a context
-    combines each tile in shared memory before touching the table.  Same rows, same sketch."""
+    sends its updates through the hot-key replicas, folded into the main table before it is read.
+    Same rows, same sketch."""
     cfg = fp.FaMockerConfig.make(seed=31, flows_per_second=300, addr_mode=addr_mode, framed=True)
     n = 120_000
     buf, offs = fp.mocker_host(cfg, 0, n)
