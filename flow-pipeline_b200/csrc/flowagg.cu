@@ -826,6 +826,21 @@ struct HhLess {
     }
 };
 
+// ---- top-K selection on the device: radix sort of the (inverted) estimates, gather the head ----
+__global__ void k_hh_sort_keys(const fa_hh *hh, uint32_t n, unsigned long long *keys, uint32_t *idx)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = ~hh[i].estimate;  // ascending sort of the complement = descending estimates
+        idx[i] = i;
+    }
+}
+__global__ void k_hh_gather(const fa_hh *hh, const uint32_t *idx, uint32_t m, fa_hh *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = hh[idx[i]];
+}
+
 extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t *n)
 {
     if (!c || !n || !c->d_cms || !c->d_slots || (k && !out)) return FA_ERR_INVALID;
@@ -838,26 +853,56 @@ extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t 
     const uint64_t groups = c->h_counters->n_groups;
     *n = 0;
     if (!groups || !k) return FA_OK;
+    if (groups >= (1ull << 31)) return FA_ERR_INVALID;
     const unsigned long long *cms = c->d_cms;
     if (which == FA_CMS_GLOBAL) {
         rc = ensure_cms_global(c);
         if (rc) return rc;
         cms = c->d_cms_global;
     }
-    rc = ensure_scratch(c, groups * sizeof(fa_hh));
+    // scratch: hh[groups] | keys_a | keys_b (u64) | idx_a | idx_b (u32) | head[m] | cub temp
+    const uint32_t ng = (uint32_t)groups;
+    const size_t kk = std::min<size_t>(k, groups);
+    const uint32_t m = (uint32_t)std::min<uint64_t>(groups, (uint64_t)kk + 4096);  // head + room for ties at the cut
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)ng, 0, 64, c->stream);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t hh_b = al(groups * sizeof(fa_hh)), k_b = al(groups * 8), i_b = al(groups * 4), head_b = al((size_t)m * sizeof(fa_hh));
+    rc = ensure_scratch(c, hh_b + 2 * k_b + 2 * i_b + head_b + al(cub_bytes));
     if (rc) return rc;
+    uint8_t *base = (uint8_t *)c->d_scratch;
+    fa_hh *d_hh = (fa_hh *)base;
+    unsigned long long *keys_a = (unsigned long long *)(base + hh_b), *keys_b = (unsigned long long *)(base + hh_b + k_b);
+    uint32_t *idx_a = (uint32_t *)(base + hh_b + 2 * k_b), *idx_b = (uint32_t *)(base + hh_b + 2 * k_b + i_b);
+    fa_hh *d_head = (fa_hh *)(base + hh_b + 2 * k_b + 2 * i_b);
+    void *cub_tmp = base + hh_b + 2 * k_b + 2 * i_b + head_b;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
     cudaError_t e;
-#define CALL_EST(K) launch_estimate<K>(c, cms, (fa_hh *)c->d_scratch, groups)
+#define CALL_EST(K) launch_estimate<K>(c, cms, d_hh, groups)
     FA_DISPATCH_KW(c->kw, CALL_EST)
 #undef CALL_EST
     FA_CUDA(c, e);
-    std::vector<fa_hh> all(groups);
-    FA_CUDA(c, cudaMemcpyAsync(all.data(), c->d_scratch, groups * sizeof(fa_hh), cudaMemcpyDeviceToHost, c->stream));
+    const int g = (int)((ng + 255) / 256);
+    k_hh_sort_keys<<<g, 256, 0, c->stream>>>(d_hh, ng, keys_a, idx_a);
+    FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, idx_a, idx_b, (int)ng, 0, 64, c->stream));
+    k_hh_gather<<<(int)((m + 255) / 256), 256, 0, c->stream>>>(d_hh, idx_b, m, d_head);
+    FA_CUDA(c, cudaGetLastError());
+    std::vector<fa_hh> head(m);
+    FA_CUDA(c, cudaMemcpyAsync(head.data(), d_head, (size_t)m * sizeof(fa_hh), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));
-    const size_t kk = std::min<size_t>(k, groups);
-    std::partial_sort(all.begin(), all.begin() + kk, all.end(), HhLess{c->kw});
-    memcpy(out, all.data(), kk * sizeof(fa_hh));
+    if (m < groups && head[m - 1].estimate == head[kk - 1].estimate) {
+        // more than 4096 candidates tie with the k-th estimate: order ALL of them on the host (exact, slow, pathological)
+        std::vector<fa_hh> all(groups);
+        FA_CUDA(c, cudaMemcpy(all.data(), d_hh, groups * sizeof(fa_hh), cudaMemcpyDeviceToHost));
+        std::partial_sort(all.begin(), all.begin() + kk, all.end(), HhLess{c->kw});
+        memcpy(out, all.data(), kk * sizeof(fa_hh));
+        *n = kk;
+        return FA_OK;
+    }
+    // the head holds every candidate that can make the cut; final order (estimate desc, key asc) on <= k+4096 rows
+    std::sort(head.begin(), head.end(), HhLess{c->kw});
+    memcpy(out, head.data(), kk * sizeof(fa_hh));
     *n = kk;
     return FA_OK;
 }

@@ -42,6 +42,14 @@ def run(name, agg, cfg, n_total, after=None):
     print(name, json.dumps(res), file=sys.stderr, flush=True)
 
 
+# kernel 1 alone: decode to the 20 columns (16.7M records)
+cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True)
+with fp.FlowAgg("flows5m", stream=stream, columns=True, aggregate=False, max_batch_records=SLAB) as a:
+    run("kernel 1 alone: decode 2^24 records to 20 columns", a, cfg, SLAB)
+    run("kernel 1 alone: decode 2^24 records to 20 columns (2nd pass)", a, cfg, SLAB)
+with fp.FlowAgg("aspair", stream=stream, columns=True, max_batch_records=SLAB, table_capacity=1 << 19) as a:
+    run("unfused K1 -> K2 (columns then aggregate), 2^24 records", a, cfg, SLAB)
+    run("unfused K1 -> K2 (columns then aggregate), 2^24 records (2nd pass)", a, cfg, SLAB)
 # mocker-native distribution: 9 AS pairs x 2 slots -> the hot-key worst case for the table atomics
 cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=250_000, framed=True)
 with fp.FlowAgg("flows5m", stream=stream) as a:

@@ -403,3 +403,84 @@ def test_hot_keys_take_the_replica_path(fp, oracle, torch_cuda, mode, addr_mode,
         if cms:
             assert np.array_equal(a.cms_read(), wcms)
         assert np.array_equal(a.flush(), want)
+
+
+def test_topk_ties_are_broken_by_key(fp, oracle, torch_cuda):
+    """20 000 distinct addresses with identical weights: thousands of estimates tie at the cut, so the
+    device-side selection has to fall back to ordering every candidate (estimate desc, key asc)."""
+    msgs = []
+    rng = np.random.default_rng(5)
+    addrs = rng.permutation(20000)
+    for a in addrs:
+        addr = bytes.fromhex("20010db800000001") + int(a).to_bytes(8, "big")
+        msgs.append(b"\x18\x01" + b"\x32\x10" + addr + b"\x48\x64")  # SamplingRate=1, SrcAddr, Bytes=100
+    blob, offs = concat_records(frame(msgs))
+    cand, cms, _ = oracle.run_batch(blob, offs, key_mode="srcaddr", cms=(4, 16))
+    want = oracle.topk(cms, 4, 16, 4, cand, 50)
+    with fp.FlowAgg("srcaddr", cms=True, cms_depth=4, cms_width_log2=16, table_capacity=1 << 16) as a:
+        a.submit(blob, offs)
+        top = a.topk_local(50)
+    assert np.array_equal(top["key"], want["key"]) and np.array_equal(top["estimate"], want["estimate"])
+    assert (np.diff(top["estimate"].astype(np.int64)) <= 0).all()
+
+
+def _nccl_worker(rank, world, port, q):
+    import importlib
+    import os
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import flow_pipeline_b200 as fp
+
+    par = importlib.import_module("flow-pipeline_b200.parallel")
+    cfg = fp.FaMockerConfig.make(seed=13, flows_per_second=1000, addr_mode=1, framed=True)
+    n_part, per = 4, 40000
+    with fp.FlowAgg("srcaddr", device=rank, cms=True, cms_width_log2=14, table_capacity=1 << 18,
+                    stream=torch.cuda.current_stream().cuda_stream) as a, fp.FlowAgg("flows5m", device=rank) as b:
+        for p in par.my_partitions(n_part, world, rank):   # Kafka partition p -> rank p mod world
+            buf, offs = fp.mocker_host(cfg, p * per, per)
+            a.submit(buf, offs)
+            b.submit(buf, offs)
+        top = par.box_topk(a, 100)                        # NCCL all-reduce of the sketches + merge
+        top2 = par.box_topk(a, 100)                       # a second query must not double count
+        rows = par.merge_rows(b.flush(), 4, device=torch.device("cuda", rank))
+    if rank == 0:
+        q.put((top.copy(), top2.copy(), rows.copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_one_process_per_gpu_box_topk_and_row_merge_over_nccl(fp, oracle, torch_cuda):
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import os
+
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    top, top2, rows = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    cfg = fp.FaMockerConfig.make(seed=13, flows_per_second=1000, addr_mode=1, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 4 * 40000)
+    cand, cms, _ = oracle.run_batch(buf, offs, key_mode="srcaddr", cms=(4, 14))
+    want = oracle.topk(cms, 4, 14, 4, cand, 100)
+    for t in (top, top2):
+        assert np.array_equal(t["key"], want["key"]) and np.array_equal(t["estimate"], want["estimate"])
+    want_rows, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
+    assert np.array_equal(rows, want_rows)
