@@ -64,6 +64,8 @@ struct Flags {
     std::string Out = "-";                // -out: flows_5m rows (TSV); "-" = stdout
     std::string Key = "flows5m";          // -key: flows5m|aspair|srcaddr|dstaddr|5tuple|srcport|dstport
     int Devices = 1;                      // -gpus: partition p runs on GPU p mod gpus
+    std::string Sink = "flows5m";         // -sink flows5m: roll-up rows (create.sh:70-87); rows: the inserter's own
+                                          //       14-column row per flow (inserter.go:51-66,142-157)
     bool DryRun = false;                  // -dry-run: walk the claims and fill slabs, no GPU, no aggregates
     bool Metrics = false;                 // -metrics: serve -metrics.addr (off by default in this mirror)
 };
@@ -123,6 +125,7 @@ static bool parse_flags(int argc, char **argv, Flags &f)
         } else if (a == "proto.fixedlen") f.FixedLen = !has || (v != "false" && v != "0");
         else if (a == "out") f.Out = val();
         else if (a == "key") f.Key = val();
+        else if (a == "sink") f.Sink = val();
         else if (a == "gpus") f.Devices = atoi(val().c_str());
         else if (a == "dry-run") f.DryRun = true;
         else if (a == "metrics") f.Metrics = true;
@@ -231,6 +234,57 @@ struct FileClaim : ConsumerGroupClaim {
     }
 };
 
+// ---- net.IP(b).String() with the "<nil>" -> "0.0.0.0" patch of inserter.go:131-140 ------------------
+static std::string ip_string(const uint8_t *p, size_t len)
+{
+    char buf[64];
+    if (len == 0) return "0.0.0.0";
+    const uint8_t *p4 = nullptr;
+    if (len == 4) p4 = p;
+    if (len == 16) {
+        bool z = true;
+        for (int i = 0; i < 10; i++) z = z && p[i] == 0;
+        if (z && p[10] == 0xff && p[11] == 0xff) p4 = p + 12;  // To4(): v4-mapped
+    }
+    if (p4) {
+        snprintf(buf, sizeof buf, "%u.%u.%u.%u", p4[0], p4[1], p4[2], p4[3]);
+        return buf;
+    }
+    if (len != 16) {  // "?" + hexString(ip)
+        std::string o = "?";
+        static const char hx[] = "0123456789abcdef";
+        for (size_t i = 0; i < len; i++) {
+            o += hx[p[i] >> 4];
+            o += hx[p[i] & 15];
+        }
+        return o;
+    }
+    int e0 = -1, e1 = -1;  // longest run of zero groups, leftmost on ties, at least two groups
+    for (int i = 0; i < 16; i += 2) {
+        int j = i;
+        while (j < 16 && p[j] == 0 && p[j + 1] == 0) j += 2;
+        if (j > i && j - i > e1 - e0) {
+            e0 = i;
+            e1 = j;
+            i = j;
+        }
+    }
+    if (e1 - e0 <= 2) e0 = e1 = -1;
+    std::string o;
+    for (int i = 0; i < 16; i += 2) {
+        if (i == e0) {
+            o += "::";
+            i = e1;
+            if (i >= 16) break;
+        } else if (i > 0) {
+            o += ':';
+        }
+        snprintf(buf, sizeof buf, "%x", (unsigned)((p[i] << 8) | p[i + 1]));
+        o += buf;
+    }
+    return o;
+}
+
 // ---- state (inserter.go:75-88) --------------------------------------------------------------------
 static const char *kKeyNames[] = {"flows5m", "aspair", "srcaddr", "dstaddr", "5tuple", "srcport", "dstport"};
 static std::atomic<uint64_t> g_inserts{0};  // the insert_count counter (inserter.go:44-49)
@@ -294,6 +348,7 @@ struct state {
                 exit(1);
             }
         }
+        if (!fl.DryRun && fl.Sink == "rows") write_flow_rows(ps);
         for (const ConsumerMessage &m : ps.pending) sess.MarkMessage(m);  // after the hand-over, not before (inserter.go:188)
         ps.pending.clear();
         g_inserts += ps.nrec;
@@ -329,7 +384,7 @@ struct state {
     {
         logf(2, "Processed %ld records in the last iteration.", msgCount.exchange(0));
         submit_slab(ps, sess);
-        if (fl.DryRun) return true;
+        if (fl.DryRun || fl.Sink == "rows") return true;
         size_t n = 0;
         std::vector<fa_row> rows(1 << 16);
         int rc = fa_flush(ps.ctx, rows.data(), rows.size(), &n, 0);
@@ -349,6 +404,41 @@ struct state {
         fflush(out);
         rows_written += n;
         return true;
+    }
+
+    // -sink rows: the reference's own output, one row per decoded flow with the columns of flow_fields
+    // (inserter.go:51-66) in the order of inserter.go:142-157; undecodable messages produce no row (:125-126)
+    void write_flow_rows(PartitionState &ps)
+    {
+        const size_t n = ps.nrec;
+        std::vector<uint8_t> valid(n), sa(n * 16), da(n * 16), sal(n), dal(n);
+        std::vector<uint64_t> tfs(n), sr(n), by(n), pk(n);
+        std::vector<uint32_t> ty(n), sp(n), dp(n), et(n), pr(n), sas(n), das(n);
+        struct { const char *name; void *dst; size_t bytes; } cols[] = {
+            {"valid", valid.data(), n}, {"src_addr", sa.data(), n * 16}, {"dst_addr", da.data(), n * 16}, {"src_addr_len", sal.data(), n},
+            {"dst_addr_len", dal.data(), n}, {"time_flow_start", tfs.data(), n * 8}, {"sampling_rate", sr.data(), n * 8}, {"bytes", by.data(), n * 8},
+            {"packets", pk.data(), n * 8}, {"type", ty.data(), n * 4}, {"src_port", sp.data(), n * 4}, {"dst_port", dp.data(), n * 4},
+            {"etype", et.data(), n * 4}, {"proto", pr.data(), n * 4}, {"src_as", sas.data(), n * 4}, {"dst_as", das.data(), n * 4}};
+        for (auto &c : cols) {
+            int rc = fa_columns_read(ps.ctx, c.name, c.dst, c.bytes);
+            if (rc) {
+                logf(0, "fa_columns_read(%s): %s (%s)", c.name, fa_strerror(rc), fa_last_error(ps.ctx));
+                exit(1);
+            }
+        }
+        std::lock_guard<std::mutex> lk(out_mu);
+        for (size_t i = 0; i < n; i++) {
+            if (!valid[i]) {
+                bad++;
+                continue;
+            }
+            // an address longer than 16 bytes is kept as its first 16 (FixedString(16), create.sh:15-16)
+            const std::string s_ip = ip_string(&sa[i * 16], sal[i] > 16 ? 16 : sal[i]), d_ip = ip_string(&da[i * 16], dal[i] > 16 ? 16 : dal[i]);
+            fprintf(out, "NOW()\t%" PRIu64 "\t%d\t%" PRIu64 "\t%s\t%s\t%" PRIu64 "\t%" PRIu64 "\t%u\t%u\t%u\t%u\t%u\t%u\n", tfs[i], (int32_t)ty[i], sr[i],
+                    s_ip.c_str(), d_ip.c_str(), by[i], pk[i], sp[i], dp[i], et[i], pr[i], sas[i], das[i]);
+            rows_written++;
+        }
+        fflush(out);
     }
 
     void write_row(const fa_row &r)
@@ -459,6 +549,7 @@ int main(int argc, char **argv)
             cfg.key_mode = (uint32_t)s.key_mode;
             cfg.max_batch_bytes = 64u << 20;
             cfg.max_batch_records = 1u << 20;
+            if (s.fl.Sink == "rows") cfg.flags = FA_CFG_COLUMNS | FA_CFG_NO_AGGREGATE;  // kernel 1 alone
             int rc = fa_create(&cfg, &parts[p].ctx);
             if (rc) {
                 logf(0, "fa_create: %s (%s)", fa_strerror(rc), parts[p].ctx ? fa_last_error(parts[p].ctx) : "");

@@ -484,3 +484,119 @@ def test_one_process_per_gpu_box_topk_and_row_merge_over_nccl(fp, oracle, torch_
         assert np.array_equal(t["key"], want["key"]) and np.array_equal(t["estimate"], want["estimate"])
     want_rows, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
     assert np.array_equal(rows, want_rows)
+
+
+def _random_wire_messages(seed, n):
+    """Wire-format fuzz that needs no schema: random tags / wire types / lengths, plus pure noise."""
+    rng = np.random.default_rng(seed)
+
+    def varint(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            if v:
+                out.append(b | 0x80)
+            else:
+                out.append(b)
+                return bytes(out)
+
+    known = [1, 2, 3, 4, 6, 7, 9, 10, 11, 14, 15, 20, 21, 22, 30, 38, 100, 101]
+    msgs = []
+    for i in range(n):
+        kind = rng.integers(0, 10)
+        if kind == 0:  # pure noise
+            msgs.append(bytes(rng.integers(0, 256, int(rng.integers(0, 60)), dtype=np.uint8)))
+            continue
+        parts = []
+        for _ in range(int(rng.integers(0, 14))):
+            num = int(rng.choice(known)) if rng.random() < 0.7 else int(rng.choice([5, 8, 16, 127, 128, 2047, 2048, 1 << 20, (1 << 29) - 1, 5, 8, 16, 0, 1 << 29]))
+            wt = int(rng.choice([0] * 12 + [2] * 8 + [1, 1, 5, 5, 3, 3, 4, 6, 7]))
+            tag = varint((num << 3) | wt)
+            if rng.random() < 0.03:
+                tag = tag[:-1] + bytes([tag[-1] | 0x80]) + b"\x00"  # over-long tag encoding
+            if wt == 0:
+                bits = int(rng.choice([1, 7, 8, 14, 21, 28, 29, 35, 36, 49, 63, 64]))
+                body = varint(int(rng.integers(0, 1 << 62)) >> (62 - min(bits, 62)) if bits < 64 else (1 << 64) - 1)
+                if rng.random() < 0.03:
+                    body = b"\xff" * 9 + bytes([int(rng.choice([0, 1, 2, 0x7f]))])
+            elif wt == 2:
+                ln = int(rng.choice([0, 1, 4, 15, 16, 17, 40, 130]))
+                payload = bytes(rng.integers(0, 256, ln, dtype=np.uint8)) if rng.random() < 0.7 else bytes(ln)
+                if num in (100, 101) and rng.random() < 0.6:
+                    payload = "héllo→日本"[: ln or 1].encode()[:ln]
+                    ln = len(payload)
+                body = varint(ln) + payload
+            elif wt == 1:
+                body = bytes(8)
+            elif wt == 5:
+                body = bytes(4)
+            elif wt == 3:
+                inner = varint((int(rng.integers(1, 50)) << 3) | 0) + varint(int(rng.integers(0, 1000)))
+                body = inner + varint((num << 3) | 4) if rng.random() < 0.8 else inner
+            else:
+                body = b""
+            parts.append(tag + body)
+        m = b"".join(parts)
+        if rng.random() < 0.1 and len(m) > 1:
+            m = m[: int(rng.integers(1, len(m)))]
+        msgs.append(m)
+    return msgs
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_schemaless_wire_fuzz_gpu_equals_oracle(fp, oracle, torch_cuda, seed):
+    msgs = _random_wire_messages(seed, 30000)
+    for framed in (False, True):
+        blob, offs = concat_records(frame(msgs) if framed else msgs)
+        ora = oracle.decode_columns(blob, offs, framed=framed)
+        gpu, st = gpu_columns(fp, blob, offs, framed=framed)
+        assert 0.2 < ora["valid"].mean() < 0.95          # the fuzz produces both kinds
+        assert_columns_equal(gpu, ora, len(msgs))
+        assert st["n_bad"] == int((ora["valid"] == 0).sum())
+    # and through the fused kernels, every key mode
+    blob, offs = concat_records(frame(msgs))
+    for mode in ("flows5m", "srcaddr", "5tuple"):
+        want, _, res = oracle.run_batch(blob, offs, key_mode=mode, scale=True)
+        with fp.FlowAgg(mode, scale_sampling=True, table_capacity=1 << 17) as a:
+            a.submit(blob, offs)
+            st = a.stats()
+            assert (st["n_bad"], st["n_nokey"]) == (res["n_bad"], res["n_nokey"])
+            assert np.array_equal(a.flush(), want)
+
+
+def test_host_inserter_mirror_row_sink_matches_the_inserters_14_columns(fp, oracle, torch_cuda, fuzz_2k, tmp_path):
+    """-sink rows: one row per decoded flow, columns and IP formatting of inserter.go:131-157
+    (net.IP.String incl. v4, v4-mapped, "?hex" and the "<nil>" -> 0.0.0.0 patch)."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "flow-pipeline_b200", "host", "flowagg-inserter")
+    g = fuzz_2k
+    msgs = [bytes(g["blob"][g["offsets"][i]:g["offsets"][i + 1]]) for i in range(len(g["offsets"]) - 1)]
+    msgs += [b"\x32\x04" + bytes([192, 168, 1, 1]) + b"\x3a\x10" + bytes(10) + b"\xff\xff" + bytes([10, 0, 0, 7]) + b"\x48\x05",
+             b"\x32\x10" + bytes.fromhex("20010db8000000010000000000000080") + b"\x3a\x03abc" + b"\xb0\x02\x8e\xb0\xdf\xf3\x05"]
+    blob, offs = concat_records(frame(msgs))
+    f = tmp_path / "claim.bin"
+    f.write_bytes(blob.tobytes())
+    out = tmp_path / "rows.tsv"
+    r = subprocess.run([exe, "-claim.file", str(f), "-sink", "rows", "-flush.count", "0", "-out", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = out.read_text().splitlines()
+    cols = oracle.decode_columns(blob, offs, framed=True)
+    want = []
+    for i in range(len(msgs)):
+        if not cols["valid"][i]:
+            continue
+        ty = int(cols["type"][i])
+        ty = ty - (1 << 32) if ty >= (1 << 31) else ty
+        sip = oracle.ip_string(bytes(cols["src_addr"][i][: min(int(cols["src_addr_len"][i]), 16)]))
+        dip = oracle.ip_string(bytes(cols["dst_addr"][i][: min(int(cols["dst_addr_len"][i]), 16)]))
+        want.append("\t".join(["NOW()", str(int(cols["time_flow_start"][i])), str(ty), str(int(cols["sampling_rate"][i])), sip, dip,
+                               str(int(cols["bytes"][i])), str(int(cols["packets"][i])), str(int(cols["src_port"][i])),
+                               str(int(cols["dst_port"][i])), str(int(cols["etype"][i])), str(int(cols["proto"][i])),
+                               str(int(cols["src_as"][i])), str(int(cols["dst_as"][i]))]))
+    assert got == want
+    assert any("\t192.168.1.1\t10.0.0.7\t" in l for l in got) and any("\t2001:db8:0:1::80\t?616263\t" in l for l in got)
