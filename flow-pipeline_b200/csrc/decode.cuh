@@ -309,7 +309,7 @@ __device__ __noinline__ uint32_t skip_other(const Src s, uint32_t pos, uint32_t 
 template <uint32_t NEED, class Src>
 __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const uint32_t end, Flow &f)
 {
-    bool zero_field = false;  // a field number 0 was seen (illegal); checked once, after the loop
+    uint32_t min_num = 1u;  // smallest field number seen: 0 is illegal; checked once, after the loop
     while (pos < end) {
         uint32_t lo, hi;
         s.window(pos, lo, hi);
@@ -341,7 +341,7 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
             pos += t.n;
             s.window(pos, xlo, xhi);  // the window restarts on the value
         }
-        zero_field |= (num == 0u);
+        min_num = min(min_num, num);
         // xlo/xhi: bytes pos.. (at least 6 valid)
         if (__builtin_expect(wt == 0, 1)) {
             // ---- varint ----
@@ -406,7 +406,7 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
     }
     // good iff the loop ended exactly on `end` (anything that ran past the record is an error)
     // and no field carried the illegal number 0
-    return pos == end && !zero_field;
+    return pos == end && min_num != 0u;
 }
 
 // Decode the record occupying [pos,end): bare message, or varint(len) || message
