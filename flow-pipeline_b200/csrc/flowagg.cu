@@ -78,6 +78,7 @@ struct fa_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
     uint64_t n_records = 0, n_submits = 0, bytes_in = 0;
+    uint64_t n_kernels = 0;  // launches of this library's own kernels (cub's are not counted)
     std::string last_error;
 };
 
@@ -133,7 +134,11 @@ static cudaError_t launch_table_init(fa_ctx *c)
     const unsigned long long words = n_slots * (SlotLayout<KW>::BYTES / 8);
     const int grid = (int)std::min<unsigned long long>((words + 255) / 256, (unsigned long long)c->num_sms * 32);
     k_table_init<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots);
-    if (c->d_hot) k_table_init<KW><<<c->num_sms, 256, 0, c->stream>>>(c->d_hot, (unsigned long long)kHotReplicas * kHotSlots);
+    c->n_kernels++;
+    if (c->d_hot) {
+        k_table_init<KW><<<c->num_sms, 256, 0, c->stream>>>(c->d_hot, (unsigned long long)kHotReplicas * kHotSlots);
+        c->n_kernels++;
+    }
     c->hot_dirty = false;
     return cudaGetLastError();
 }
@@ -152,6 +157,7 @@ static cudaError_t launch_merge_hot(fa_ctx *c)
     SubmitParams p{};
     fill_table_params(c, p);
     k_merge_hot<KW><<<c->num_sms, 256, 0, c->stream>>>(p, kHotReplicas * kHotSlots);
+    c->n_kernels++;
     return cudaGetLastError();
 }
 
@@ -342,6 +348,7 @@ static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_til
         configured = kTileBytesMax + kTilePad + 16;
     }
     k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
+    c->n_kernels++;
     return cudaGetLastError();
 }
 
@@ -364,6 +371,7 @@ template <int MODE>
 static cudaError_t launch_agg_columns_mode(fa_ctx *c, const SubmitParams &p, int grid)
 {
     k_aggregate_columns<MODE><<<grid, kThreads, 0, c->stream>>>(p, c->cols);
+    c->n_kernels++;
     return cudaGetLastError();
 }
 
@@ -603,6 +611,7 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
     out->n_groups = c->h_counters->n_groups;
     out->n_submits = c->n_submits;
     out->bytes_in = c->bytes_in;
+    out->n_kernels = c->n_kernels;
     return FA_OK;
 }
 
@@ -616,6 +625,7 @@ static cudaError_t launch_compact(fa_ctx *c, fa_row *d_rows, unsigned long long 
     const unsigned long long n_slots = c->capacity + 1;  // + the side slot
     const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
     k_compact_rows<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, d_rows, cap, c->d_counters);
+    c->n_kernels++;
     return cudaGetLastError();
 }
 
@@ -626,6 +636,7 @@ static cudaError_t launch_estimate(fa_ctx *c, const unsigned long long *cms, fa_
     const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
     k_estimate<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, cms, c->cfg.cms_depth, c->cfg.cms_width_log2, d_out, cap,
                                                 c->d_counters);
+    c->n_kernels++;
     return cudaGetLastError();
 }
 
@@ -692,12 +703,15 @@ static int sort_rows_device(fa_ctx *c, size_t groups, fa_row **sorted)
     void *cub_tmp = base + 2 * rows_b + 4 * u32_b;
     const int g = (int)((n + 255) / 256);
     k_iota<<<g, 256, 0, c->stream>>>(perm_a, n);
+    c->n_kernels++;
     for (int w = c->kw - 1; w >= 0; w--) {
         k_sort_key<<<g, 256, 0, c->stream>>>(rows_in, perm_a, n, w, keys_a);
+        c->n_kernels++;
         FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, perm_a, perm_b, (int)n, 0, 32, c->stream));
         std::swap(perm_a, perm_b);
     }
     k_gather_rows<<<g, 256, 0, c->stream>>>(rows_in, perm_a, n, rows_out);
+    c->n_kernels++;
     FA_CUDA(c, cudaGetLastError());
     *sorted = rows_out;
     return FA_OK;
@@ -772,6 +786,7 @@ extern "C" int fa_reset(fa_ctx *c)
     FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     c->n_records = c->n_submits = c->bytes_in = 0;
+    c->n_kernels = 0;
     return fa_sync(c);
 }
 
@@ -885,8 +900,10 @@ extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t 
     FA_CUDA(c, e);
     const int g = (int)((ng + 255) / 256);
     k_hh_sort_keys<<<g, 256, 0, c->stream>>>(d_hh, ng, keys_a, idx_a);
+    c->n_kernels++;
     FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, idx_a, idx_b, (int)ng, 0, 64, c->stream));
     k_hh_gather<<<(int)((m + 255) / 256), 256, 0, c->stream>>>(d_hh, idx_b, m, d_head);
+    c->n_kernels++;
     FA_CUDA(c, cudaGetLastError());
     std::vector<fa_hh> head(m);
     FA_CUDA(c, cudaMemcpyAsync(head.data(), d_head, (size_t)m * sizeof(fa_hh), cudaMemcpyDeviceToHost, c->stream));
@@ -1158,6 +1175,7 @@ extern "C" int fa_mocker_device(fa_ctx *c, const fa_mocker_config *cfg, uint64_t
     if (n == 0) return FA_OK;
     const int grid = (int)((n + 255) / 256);
     k_mocker_len<<<grid, 256, 0, c->stream>>>(*cfg, first, n, d_offsets);
+    c->n_kernels++;
     FA_CUDA(c, cudaGetLastError());
     size_t tmp = 0;
     FA_CUDA(c, cub::DeviceScan::InclusiveSum(nullptr, tmp, d_offsets + 1, d_offsets + 1, (int)n, c->stream));
@@ -1170,6 +1188,7 @@ extern "C" int fa_mocker_device(fa_ctx *c, const fa_mocker_config *cfg, uint64_t
     *bytes = total;
     if (total > cap) return FA_ERR_CAPACITY;
     k_mocker_put<<<grid, 256, 0, c->stream>>>(*cfg, first, n, d_offsets, d_buf);
+    c->n_kernels++;
     FA_CUDA(c, cudaGetLastError());
     FA_CUDA(c, cudaStreamSynchronize(c->stream));
     return FA_OK;

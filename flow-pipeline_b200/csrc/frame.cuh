@@ -158,13 +158,16 @@ static int frame_index_device(fa_ctx *c, const uint8_t *d_buf, size_t len, uint3
 
     const int tpb = 256;
     k_frame_speculate<<<(n_tiles * 32 + tpb - 1) / tpb, tpb, 0, c->stream>>>(d_buf, len, n_tiles, entry, dirty);
+    c->n_kernels++;
     FA_CUDA(c, cudaGetLastError());
     const int g = (int)((n_tiles + tpb - 1) / tpb);
     for (uint32_t round = 0;; round++) {
         k_frame_walk<<<g, tpb, 0, c->stream>>>(d_buf, len, n_tiles, entry, exit_pos, count, dirty);
+        c->n_kernels++;
         FA_CUDA(c, cudaGetLastError());
         FA_CUDA(c, cudaMemsetAsync(n_dirty, 0, 4, c->stream));
         k_frame_verify<<<g, tpb, 0, c->stream>>>(n_tiles, entry, exit_pos, dirty, n_dirty);
+        c->n_kernels++;
         FA_CUDA(c, cudaGetLastError());
         uint32_t nd = 0;
         FA_CUDA(c, cudaMemcpyAsync(&nd, n_dirty, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -190,6 +193,7 @@ static int frame_index_device(fa_ctx *c, const uint8_t *d_buf, size_t len, uint3
         c->frame_off_cap = cap;
     }
     k_frame_emit<<<g, tpb, 0, c->stream>>>(d_buf, len, n_tiles, entry, base, total, c->d_frame_off);
+    c->n_kernels++;
     FA_CUDA(c, cudaGetLastError());
     *n_found = total;
     return FA_OK;

@@ -6,7 +6,7 @@
 //   k_tile<ColConsumer>          kernel 1 alone: bytes -> 20 decoded columns in HBM
 //                                (inserter.go:142-157 row + create.sh:36-59 columns).
 //   k_aggregate_columns<MODE>    kernel 2 alone: columns -> group table (+ sketch).
-//   k_table_init / k_compact_rows / k_estimate   table reset, flush, top-K candidates.
+//   k_table_init / k_merge_hot / k_compact_rows / k_estimate   table reset, hot-replica fold, flush, top-K candidates.
 //
 // Tile kernel: one CTA = one tile of <= 256 records.  The tile's byte span is
 // brought into shared memory by ONE bulk-async copy (cp.async.bulk, the 1-D TMA

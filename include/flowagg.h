@@ -113,6 +113,7 @@ typedef struct fa_stats {
     uint64_t n_groups;   /* occupied group-table slots */
     uint64_t n_submits;  /* kernel launches of the decode/aggregate kernel */
     uint64_t bytes_in;   /* input bytes consumed */
+    uint64_t n_kernels;  /* launches of the library's own CUDA kernels (all kinds) */
 } fa_stats;
 
 /* Decoded columns of the LAST submit (FA_CFG_COLUMNS).  Device pointers, valid
