@@ -74,7 +74,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -220,7 +220,10 @@ def main():
     in_bytes = sum(s[3] for s in slabs)
     alg_bytes = in_bytes + 4 * (n_flows + len(slabs))  # records once + the offsets array
 
+    dbg = {"submit_s": 0.0, "flush_s": 0.0} if os.environ.get("BENCH_DEBUG") else None
+
     def step_device(per_launch=None):
+        t_a = time.perf_counter()
         for (d_buf, d_off, n, nb) in slabs:
             if per_launch is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,7 +232,12 @@ def main():
             if per_launch is not None:
                 e1.record()
                 per_launch.append((e0, e1, nb + 4 * (n + 1)))
-        return agg.flush()
+        t_b = time.perf_counter()
+        out_rows = agg.flush()
+        if dbg is not None and per_launch is not None:
+            dbg["submit_s"] += t_b - t_a
+            dbg["flush_s"] += time.perf_counter() - t_b
+        return out_rows
 
     def barrier():
         if world > 1:
@@ -237,13 +245,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: HBM-resident input ----
+    # The clock sampler (nvidia-smi -lms, the recipe's command) is started BEFORE the warm-up: its NVML start-up
+    # enumerates every GPU of the box and stalls launches on all of them for a moment, which must not land in a
+    # timed region.  It then runs through both timed regions (value and e2e).
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        time.sleep(1.0)
     rows = None
     for _ in range(args.warmup):
         rows = step_device()
     assert rows is not None and int(rows["count"].sum()) == n_flows and len(rows) == 65536
     launches0 = agg.stats()["n_kernels"]
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     per_launch = []
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -252,7 +265,9 @@ def main():
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
-    clocks = sampler.stop() if sampler else None
+    if dbg is not None:
+        print(f"[bench debug] rank {rank}: {ms / args.steps:.3f} ms/step; host time per step: submits {1e3 * dbg['submit_s'] / args.steps:.3f} ms, "
+              f"flush {1e3 * dbg['flush_s'] / args.steps:.3f} ms", file=sys.stderr, flush=True)
     gpu_launches = agg.stats()["n_kernels"] - launches0  # every launch of the library's own kernels in the timed region
     assert int(rows["count"].sum()) == n_flows
     if world > 1:
@@ -304,6 +319,8 @@ def main():
                "note": "pinned host buffers -> fa_submit (256 MiB batches, copy/compute overlapped) -> fa_flush rows on host"}
         eagg.close()
         del hslabs
+
+    clocks = sampler.stop() if sampler else None  # samples cover the warm-up and both timed regions
 
     # ---- CPU baseline on the box's host cores (rank 0, bounded sample) ----
     cpu = None
