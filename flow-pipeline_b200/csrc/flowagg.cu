@@ -720,9 +720,11 @@ static int sort_rows_device(fa_ctx *c, size_t groups, fa_row **sorted)
 extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
 {
     if (!c || !n || !c->d_slots) return FA_ERR_INVALID;
-    int rc = fa_sync(c);
-    if (rc) return rc;
-    rc = merge_hot(c);
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    // everything submitted so far is ordered before this on the context's stream (copies hand over through
+    // events), so no host-side wait is needed before enqueueing: two synchronisations in all, one to learn the
+    // row count, one for the rows
+    int rc = merge_hot(c);
     if (rc) return rc;
     rc = read_counters(c);
     if (rc) return rc;
