@@ -138,7 +138,7 @@ def host_slabs(fp, cfg, first, n_flows, slab):
         return list(ex.map(lambda j: fp.mocker_host(cfg, j[0], j[1]), jobs))
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the CPU restatement of the reference path on the host cores (rank 0 only)."""
     if rank != 0:
         return 0
@@ -168,7 +168,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -184,9 +184,17 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version banner ...)
+    # is sent to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, emit)
 
     import torch
     import torch.distributed as dist
@@ -194,7 +202,7 @@ def main():
     import flow_pipeline_b200 as fp
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device; libflowagg has no CPU fallback"}))
+        emit({"error": "no CUDA device; libflowagg has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -221,6 +229,10 @@ def main():
     alg_bytes = in_bytes + 4 * (n_flows + len(slabs))  # records once + the offsets array
 
     dbg = {"submit_s": 0.0, "flush_s": 0.0} if os.environ.get("BENCH_DEBUG") else None
+    # the caller-owned row array, reused by every flush like a Go host reuses its slice; pinned, so the rows land
+    # in it straight from the device
+    rows_pin = torch.empty(70_000 * fp.ROW_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    rows_out = rows_pin.numpy().view(fp.ROW_DTYPE)
 
     def step_device(per_launch=None):
         t_a = time.perf_counter()
@@ -233,7 +245,7 @@ def main():
                 e1.record()
                 per_launch.append((e0, e1, nb + 4 * (n + 1)))
         t_b = time.perf_counter()
-        out_rows = agg.flush()
+        out_rows = agg.flush(out=rows_out)
         if dbg is not None and per_launch is not None:
             dbg["submit_s"] += t_b - t_a
             dbg["flush_s"] += time.perf_counter() - t_b
@@ -270,6 +282,7 @@ def main():
               f"flush {1e3 * dbg['flush_s'] / args.steps:.3f} ms", file=sys.stderr, flush=True)
     gpu_launches = agg.stats()["n_kernels"] - launches0  # every launch of the library's own kernels in the timed region
     assert int(rows["count"].sum()) == n_flows
+    rows = rows.copy()  # rows_out is reused by the e2e leg
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -296,10 +309,11 @@ def main():
         def step_e2e():
             for (hb, ho, n, nb) in hslabs:
                 eagg.submit(hb, ho, framed=True, n_records=n, nbytes=nb)
-            return eagg.flush()
+            return eagg.flush(out=rows_out)
 
         for _ in range(args.warmup):
             erows = step_e2e()
+        erows = erows.copy()
         assert np.array_equal(erows, rows)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -365,7 +379,7 @@ def main():
                          "launches_timed": len(k_ms), "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     agg.close()
     if world > 1:
         dist.barrier()

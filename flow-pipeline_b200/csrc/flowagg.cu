@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <mutex>
@@ -721,6 +722,14 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
 {
     if (!c || !n || !c->d_slots) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    static const bool dbg = getenv("FA_DEBUG_FLUSH") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+    };
+    const auto t_in = now();
+    if (dbg) cudaStreamSynchronize(c->stream);  // separates "waiting for the submitted kernels" from the flush itself
+    const auto t_start = now();
     // everything submitted so far is ordered before this on the context's stream (copies hand over through
     // events), so no host-side wait is needed before enqueueing: two synchronisations in all, one to learn the
     // row count, one for the rows
@@ -730,6 +739,7 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
     if (rc) return rc;
     const uint64_t groups = c->h_counters->n_groups;
     const uint64_t dropped = c->h_counters->n_dropped;
+    const auto t_count = now();
     *n = (size_t)groups;
     if (groups > cap || (groups && !rows)) return FA_ERR_CAPACITY;
     if (groups >= (1ull << 31)) return FA_ERR_INVALID;
@@ -749,7 +759,12 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
             if (rc) return rc;
         }
         const size_t bytes = groups * sizeof(fa_row);
-        if (bytes <= (256u << 20)) {  // land in pinned memory, then one host memcpy into the caller's array
+        // a pinned destination (cudaHostAlloc / cudaHostRegister / a torch pinned tensor) takes the rows directly;
+        // pageable memory goes through the context's pinned landing area and one host memcpy
+        cudaPointerAttributes attr{};
+        const bool pinned_dst = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();  // an unregistered pointer is reported as an error on some drivers: not ours to keep
+        if (!pinned_dst && bytes <= (256u << 20)) {
             if (bytes > c->bounce_bytes) {
                 if (c->h_bounce) cudaFreeHost(c->h_bounce);
                 c->h_bounce = nullptr;
@@ -763,8 +778,13 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
                 rc = reset_table(c);  // overlaps the copy on the same stream order
                 if (rc) return rc;
             }
+            const auto t_enq = now();
             FA_CUDA(c, cudaStreamSynchronize(c->stream));
+            const auto t_sync = now();
             memcpy(rows, c->h_bounce, bytes);
+            if (dbg)
+                fprintf(stderr, "[fa_flush] wait-for-kernels %ld us | merge+count %ld us | enqueue compact/sort/copy/reset %ld us | device work + sync %ld us | memcpy %ld us\n",
+                        us(t_in, t_start), us(t_start, t_count), us(t_count, t_enq), us(t_enq, t_sync), us(t_sync, now()));
             return dropped ? FA_ERR_TABLE_FULL : FA_OK;
         }
         FA_CUDA(c, cudaMemcpyAsync(rows, src, bytes, cudaMemcpyDeviceToHost, c->stream));

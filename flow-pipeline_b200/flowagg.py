@@ -237,19 +237,23 @@ class FlowAgg:
         return {k: int(getattr(s, k)) for k, _ in FaStats._fields_}
 
     # -- emit (inserter.go:90-111 -> flows_5m rows, create.sh:70-110)
-    def flush(self, keep=False, sort=True, allow_full=False):
+    def flush(self, keep=False, sort=True, allow_full=False, out=None):
+        """Roll-up rows in ORDER BY order.  out: a caller-owned ROW_DTYPE array to fill and reuse across flushes,
+        the way a C/Go caller reuses its row slice (pinned memory receives the rows without a staging copy);
+        the returned array is then a view of it."""
         flags = (FA_FLUSH_KEEP if keep else 0) | (0 if sort else FA_FLUSH_UNSORTED)
         ok = (0, -5) if allow_full else (0,)
         n = C.c_size_t()
-        cap = getattr(self, "_rows_cap", 1 << 16)
+        cap = len(out) if out is not None else getattr(self, "_rows_cap", 1 << 16)
         while True:
-            rows = np.empty(cap, dtype=ROW_DTYPE)
-            rc = self._L.fa_flush(self._h, rows.ctypes.data, cap, C.byref(n), flags)
-            if rc == -4 and n.value > cap:  # FA_ERR_CAPACITY: nothing was reset, retry with the size it reported
+            rows = out if out is not None and len(out) >= cap else np.empty(cap, dtype=ROW_DTYPE)
+            rc = self._L.fa_flush(self._h, rows.ctypes.data, len(rows), C.byref(n), flags)
+            if rc == -4 and n.value > len(rows):  # FA_ERR_CAPACITY: nothing was reset, retry with the size it reported
                 cap = n.value
+                out = None
                 continue
             self._check(rc, "fa_flush", ok)
-            self._rows_cap = max(cap, 1 << 16)
+            self._rows_cap = max(len(rows), 1 << 16)
             return rows[: n.value]
 
     def reset(self):
