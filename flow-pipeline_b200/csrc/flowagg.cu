@@ -342,11 +342,12 @@ template <class Consumer, int THREADS>
 static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
     const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;  // tile buffer + over-read pad + mbarrier
-    static thread_local size_t configured = 0;  // per kernel instantiation and host thread
-    if (smem > 48 * 1024 && smem > configured) {
+    static thread_local unsigned long long configured = 0;  // bit d: done for device d (per kernel instantiation, per thread)
+    const unsigned long long dev_bit = 1ull << (c->cfg.device & 63);
+    if (smem > 48 * 1024 && !(configured & dev_bit)) {  // the attribute is per device
         cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
         if (e != cudaSuccess) return e;
-        configured = kTileBytesMax + kTilePad + 16;
+        configured |= dev_bit;
     }
     k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
     c->n_kernels++;
