@@ -79,6 +79,7 @@ struct fa_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
     uint64_t n_records = 0, n_submits = 0, bytes_in = 0;
+    uint64_t last_groups = 0;  // rows of the previous flush: sizes the speculative (single-sync) flush
     uint64_t n_kernels = 0;  // launches of this library's own kernels (cub's are not counted)
     std::string last_error;
 };
@@ -671,6 +672,15 @@ __global__ void k_sort_key(const fa_row *rows, const uint32_t *perm, uint32_t n,
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = rows[perm[i]].key[word];
 }
+// speculative variant: only the first counters->flush_rows rows exist; the rest of [0,n) sorts to the end
+__global__ void k_sort_key_guarded(const fa_row *rows, const uint32_t *perm, uint32_t n, int word, uint32_t *keys, const Counters *counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t src = perm[i];
+        keys[i] = (unsigned long long)src < counters->flush_rows ? rows[src].key[word] : 0xFFFFFFFFu;
+    }
+}
 __global__ void k_gather_rows(const fa_row *in, const uint32_t *perm, uint32_t n, fa_row *out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -719,6 +729,82 @@ static int sort_rows_device(fa_ctx *c, size_t groups, fa_row **sorted)
     return FA_OK;
 }
 
+// Steady-state flush with ONE synchronisation.  The row count is guessed from the previous flush (a 5-minute
+// roll-up has about as many groups as the last one), so compaction, ORDER BY and the copies are all enqueued at
+// once -- behind the kernels that are still running -- and the host waits a single time.  Compaction keeps
+// every row in scratch, so a wrong guess loses nothing: *done stays false and the exact path re-reads them.
+static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags, bool *done)
+{
+    *done = false;
+    const uint64_t all_rows = c->capacity + 1;                     // compaction bound
+    const uint64_t m64 = std::min<uint64_t>({(uint64_t)cap, all_rows, c->last_groups + c->last_groups / 8 + 256});
+    if (all_rows > (1ull << 22) || m64 < c->last_groups || m64 >= (1ull << 31)) return FA_OK;  // big tables / small caller array: exact path
+    const uint32_t m = (uint32_t)m64;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)m,
+                                    0, 32, c->stream);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t in_b = al(all_rows * sizeof(fa_row)), out_b = al((size_t)m * sizeof(fa_row)), u32_b = al((size_t)m * 4);
+    int rc = ensure_scratch(c, in_b + out_b + 4 * u32_b + al(cub_bytes));
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)c->d_scratch;
+    fa_row *rows_in = (fa_row *)base, *rows_out = (fa_row *)(base + in_b);
+    uint32_t *keys_a = (uint32_t *)(base + in_b + out_b), *keys_b = (uint32_t *)(base + in_b + out_b + u32_b);
+    uint32_t *perm_a = (uint32_t *)(base + in_b + out_b + 2 * u32_b), *perm_b = (uint32_t *)(base + in_b + out_b + 3 * u32_b);
+    void *cub_tmp = base + in_b + out_b + 4 * u32_b;
+    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+    cudaError_t e;
+#define CALL_COMPACT(K) launch_compact<K>(c, rows_in, all_rows)
+    FA_DISPATCH_KW(c->kw, CALL_COMPACT)
+#undef CALL_COMPACT
+    FA_CUDA(c, e);
+    const int g = (int)((m + 255) / 256);
+    k_iota<<<g, 256, 0, c->stream>>>(perm_a, m);
+    c->n_kernels++;
+    for (int w = c->kw - 1; w >= 0; w--) {
+        k_sort_key_guarded<<<g, 256, 0, c->stream>>>(rows_in, perm_a, m, w, keys_a, c->d_counters);
+        c->n_kernels++;
+        FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, perm_a, perm_b, (int)m, 0, 32, c->stream));
+        std::swap(perm_a, perm_b);
+    }
+    k_gather_rows<<<g, 256, 0, c->stream>>>(rows_in, perm_a, m, rows_out);  // entries past the true count are never read
+    c->n_kernels++;
+    FA_CUDA(c, cudaGetLastError());
+    const size_t bytes = (size_t)m * sizeof(fa_row);
+    cudaPointerAttributes attr{};
+    const bool pinned_dst = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    void *dst = rows;
+    if (!pinned_dst) {
+        if (bytes > c->bounce_bytes) {
+            if (c->h_bounce) cudaFreeHost(c->h_bounce);
+            c->h_bounce = nullptr;
+            c->bounce_bytes = 0;
+            const size_t want = std::max<size_t>(bytes * 2, 1u << 20);
+            FA_CUDA(c, cudaHostAlloc(&c->h_bounce, want, cudaHostAllocDefault));
+            c->bounce_bytes = want;
+        }
+        dst = c->h_bounce;
+    }
+    FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaMemcpyAsync(dst, rows_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaStreamSynchronize(c->stream));  // the one wait
+    const uint64_t groups = c->h_counters->n_groups, dropped = c->h_counters->n_dropped;
+    if (groups > m) {  // the roll-up grew by more than 1/8: every row is still in scratch, the exact path takes over
+        c->last_groups = groups;
+        return FA_OK;
+    }
+    c->last_groups = groups;
+    *n = (size_t)groups;
+    if (!pinned_dst) memcpy(rows, c->h_bounce, (size_t)groups * sizeof(fa_row));
+    if (!(flags & FA_FLUSH_KEEP)) {
+        rc = reset_table(c);  // enqueued only now that the rows are safely on the host; the next submit queues behind it
+        if (rc) return rc;
+    }
+    *done = true;
+    return dropped ? FA_ERR_TABLE_FULL : FA_OK;
+}
+
 extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
 {
     if (!c || !n || !c->d_slots) return FA_ERR_INVALID;
@@ -732,14 +818,20 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
     if (dbg) cudaStreamSynchronize(c->stream);  // separates "waiting for the submitted kernels" from the flush itself
     const auto t_start = now();
     // everything submitted so far is ordered before this on the context's stream (copies hand over through
-    // events), so no host-side wait is needed before enqueueing: two synchronisations in all, one to learn the
-    // row count, one for the rows
+    // events), so no host-side wait is needed before enqueueing
     int rc = merge_hot(c);
     if (rc) return rc;
+    if (!(flags & FA_FLUSH_UNSORTED) && c->last_groups && rows) {
+        bool done = false;
+        rc = flush_speculative(c, rows, cap, n, flags, &done);
+        if (rc || done) return rc;
+    }
+    // exact path: two synchronisations, one to learn the row count, one for the rows
     rc = read_counters(c);
     if (rc) return rc;
     const uint64_t groups = c->h_counters->n_groups;
     const uint64_t dropped = c->h_counters->n_dropped;
+    c->last_groups = groups;
     const auto t_count = now();
     *n = (size_t)groups;
     if (groups > cap || (groups && !rows)) return FA_ERR_CAPACITY;

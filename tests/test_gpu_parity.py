@@ -600,3 +600,20 @@ def test_host_inserter_mirror_row_sink_matches_the_inserters_14_columns(fp, orac
                                str(int(cols["src_as"][i])), str(int(cols["dst_as"][i]))]))
     assert got == want
     assert any("\t192.168.1.1\t10.0.0.7\t" in l for l in got) and any("\t2001:db8:0:1::80\t?616263\t" in l for l in got)
+
+
+def test_repeated_flushes_speculative_row_count(fp, oracle, torch_cuda):
+    """From the second flush on the row count is guessed from the previous flush (one synchronisation);
+    a roll-up that grows, shrinks or stays must still come back exact and ordered."""
+    sizes = [(3, 2000), (3, 2000), (64, 50000), (64, 50000), (2, 500), (200, 120000), (200, 120000)]
+    with fp.FlowAgg("flows5m", table_capacity=1 << 17) as a:
+        first = 0
+        for n_as, n in sizes:
+            cfg = fp.FaMockerConfig.make(seed=17, flows_per_second=37, n_src_as=n_as, n_dst_as=n_as, framed=True)
+            buf, offs = fp.mocker_host(cfg, first, n)
+            first += n
+            want, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
+            a.submit(buf, offs)
+            got = a.flush()
+            assert np.array_equal(got, want), (n_as, n, len(got), len(want))
+            assert a.stats()["n_groups"] == 0
