@@ -40,9 +40,10 @@ WORKLOAD = "configs[1]: 100M mocker FlowMessages, (SrcAS,DstAS) group-by sum(Byt
 METRIC = "flows/sec aggregated (decode+aggregate); achieved HBM GB/s vs peak"
 
 
-def mocker_cfg(fp):
-    # 250k flows/s of stream time: 100M flows span 400 s = two five-minute slots
-    return fp.FaMockerConfig.make(seed=1, flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True)
+def mocker_cfg(fp, partition=0):
+    # 250k flows/s of stream time: 100M flows span 400 s = two five-minute slots.  One mocker instance per Kafka
+    # partition: its own random stream (seed) and its own SequenceNum counter from 0 (`var i uint32`, mocker/mocker.go:52,89)
+    return fp.FaMockerConfig.make(seed=1 + partition, flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True)
 
 
 def measured_peak():
@@ -181,6 +182,8 @@ def main():
     ap.add_argument("--flows", type=int, default=N_FLOWS, help=argparse.SUPPRESS)  # smaller runs under ncu only
     ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--partition", type=int, default=None, help=argparse.SUPPRESS)  # which producer instance (default: rank)
+    ap.add_argument("--first", type=int, default=0, help=argparse.SUPPRESS)  # first SequenceNum (>= 2^28: 5-byte varints, 86-byte records)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,13 +213,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n_flows = args.flows
-    cfg = mocker_cfg(fp)
+    partition = rank if args.partition is None else args.partition
+    cfg = mocker_cfg(fp, partition)
     stream = torch.cuda.current_stream().cuda_stream
     agg = fp.FlowAgg("aspair", device=local_rank, stream=stream, table_capacity=TABLE_CAP)
 
     # ---- synthetic input, generated where it is consumed (partition = rank) ----
     slabs = []
-    first = rank * n_flows
+    first = args.first  # SequenceNum of the partition's first flow (0: a freshly started producer)
     done = 0
     while done < n_flows:
         n = min(SLAB, n_flows - done)
@@ -278,6 +282,13 @@ def main():
     barrier()
     ms = t0.elapsed_time(t1)
     if dbg is not None:
+        k_avg = sum(a.elapsed_time(b) for a, b, _ in per_launch) / max(len(per_launch), 1)
+        try:
+            smi = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,pci.bus_id",
+                                  "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        except Exception as ex:
+            smi = str(ex)
+        print(f"[bench debug] rank {rank}: fused kernel avg {k_avg:.4f} ms/launch; idle-after-run nvidia-smi: {smi}", file=sys.stderr, flush=True)
         print(f"[bench debug] rank {rank}: {ms / args.steps:.3f} ms/step; host time per step: submits {1e3 * dbg['submit_s'] / args.steps:.3f} ms, "
               f"flush {1e3 * dbg['flush_s'] / args.steps:.3f} ms", file=sys.stderr, flush=True)
     gpu_launches = agg.stats()["n_kernels"] - launches0  # every launch of the library's own kernels in the timed region
@@ -370,7 +381,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "flows_per_step_per_gpu": n_flows, "input_bytes_per_step_per_gpu": int(in_bytes),
-                       "key": "(SrcAS,DstAS)", "groups": 65536, "slab_records": SLAB, "partitioning": "kafka partition = rank",
+                       "key": "(SrcAS,DstAS)", "groups": 65536, "slab_records": SLAB, "partitioning": "kafka partition = rank, one mocker instance (own seed, SequenceNum from 0) per partition",
                        "l2": "inputs (8.4 GB) larger than L2, streamed with L2 evict-first; the 16 MiB group table stays L2-resident by design", "table_slots": TABLE_CAP,
                        "step": "fused decode+aggregate of every slab + flush (compact, D2H, ORDER BY on host)",
                        "box_merge": "per-rank roll-ups; the cross-rank row merge happens per 5-minute flush, outside the timed region"},

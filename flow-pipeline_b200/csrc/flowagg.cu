@@ -389,6 +389,26 @@ static cudaError_t launch_agg_columns_mode(fa_ctx *c, const SubmitParams &p, int
     default: e = CALL(FA_KEY_DSTPORT); break;              \
     }
 
+// Shared-memory bank conflicts of the record cursors: lane j of a warp starts at byte ~ j*d*avg of the tile, so
+// near-constant record sizes with avg/4 close to a multiple of 32/k words put every k-th lane on one bank (mocker
+// records of 86 B: 11 lanes per bank at d = 1).  Choose the record stride d between neighbouring lanes
+// that minimises the worst start-bank multiplicity; ties keep the smaller d (coalesced offset loads).
+static uint32_t pick_lane_stride(double avg)
+{
+    static const int forced = getenv("FA_LANE_STRIDE") ? atoi(getenv("FA_LANE_STRIDE")) : 0;
+    if (forced > 0 && forced < 128 && ((forced & 1) || forced == 2 || forced == 4 || forced == 8)) return (uint32_t)forced;
+    uint32_t best_d = 1, best_conf = 33;
+    for (uint32_t d = 1; d <= 8; d *= 2) {
+        uint32_t cnt[32] = {0}, conf = 0;
+        for (uint32_t j = 0; j < 32; j++) conf = std::max(conf, ++cnt[(uint32_t)((double)(j * d) * avg / 4.0) & 31u]);
+        if (conf < best_conf) {
+            best_conf = conf;
+            best_d = d;
+        }
+    }
+    return best_d;
+}
+
 // Launch decode(+aggregate) over records already in device memory.
 static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t len, const uint32_t *d_offsets,
                         uint32_t n_records, uint32_t flags)
@@ -422,6 +442,7 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     if (tb < 4096u) tb = 4096u;
     p.tile_records = tr;
     p.tile_bytes = tb;
+    p.lane_stride = pick_lane_stride(avg);
     tp.c = c->cols;
     const uint32_t n_tiles = (n_records + tr - 1) / tr;
     cudaError_t e = cudaSuccess;

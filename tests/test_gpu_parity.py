@@ -1,5 +1,7 @@
 """GPU parity: the sm_100a kernels, driven through the C ABI (include/flowagg.h), against the
 CPU oracle and the golden vectors.  Bit-exact: everything on this path is integer/byte work."""
+import os
+
 import numpy as np
 import pytest
 
@@ -617,3 +619,36 @@ def test_repeated_flushes_speculative_row_count(fp, oracle, torch_cuda):
             got = a.flush()
             assert np.array_equal(got, want), (n_as, n, len(got), len(want))
             assert a.stats()["n_groups"] == 0
+
+
+_STRIDE_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import flow_pipeline_b200 as fp
+from oracle import oracle
+cfg = fp.FaMockerConfig.make(seed=9, flows_per_second=250_000, n_src_as=64, n_dst_as=64, framed=True)
+buf, offs = fp.mocker_host(cfg, {first}, 70_001)          # 273 full tiles of 256 records and a ragged tail
+for mode in ("aspair", "flows5m"):
+    want, _, _ = oracle.run_batch(buf, offs, key_mode=mode)
+    with fp.FlowAgg(mode, table_capacity=1 << 16) as a:
+        a.submit(buf, offs)
+        assert a.stats()["n_bad"] == 0
+        assert np.array_equal(a.flush(), want), mode
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("stride,first", [("", 0), ("", 300_000_000), ("2", 0), ("4", 300_000_000), ("8", 0), ("7", 300_000_000), ("37", 0)])
+def test_record_to_lane_stride_is_result_neutral(torch_cuda, stride, first):
+    """The host picks how many records lie between neighbouring lanes of a warp (shared-memory bank conflicts of
+    near-constant record sizes: SequenceNum >= 2^28 makes every mocker record 85-86 bytes, 11 lanes per bank).
+    Whatever it picks -- or FA_LANE_STRIDE forces -- every record is decoded exactly once: same rows."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.pop("FA_LANE_STRIDE", None)
+    if stride:
+        env["FA_LANE_STRIDE"] = stride
+    r = subprocess.run([sys.executable, "-c", _STRIDE_SNIPPET.format(root=root, first=first)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
