@@ -123,6 +123,16 @@ def usable_cores():
     return n
 
 
+def cgroup_throttle():
+    """(nr_throttled, throttled_usec) of this cgroup: non-zero growth across a timed region means the box's CPU
+    quota, not the GPU, stretched it."""
+    try:
+        kv = dict(l.split() for l in open("/sys/fs/cgroup/cpu.stat").read().splitlines())
+        return int(kv.get("nr_throttled", 0)), int(kv.get("throttled_usec", 0))
+    except Exception:
+        return None
+
+
 def cpu_oracle_run(slabs, threads):
     """The CPU restatement (oracle/flow_oracle.c) over host slabs [(bytes, offsets)], all threads."""
     from oracle import oracle as o
@@ -276,8 +286,11 @@ def main():
     per_launch = []
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    step_wall, throttle0 = [], cgroup_throttle()
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         rows = step_device(per_launch)
+        step_wall.append(1e3 * (time.perf_counter() - t_s))  # every step ends in the flush's sync
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
@@ -289,6 +302,8 @@ def main():
         except Exception as ex:
             smi = str(ex)
         print(f"[bench debug] rank {rank}: fused kernel avg {k_avg:.4f} ms/launch; idle-after-run nvidia-smi: {smi}", file=sys.stderr, flush=True)
+        print(f"[bench debug] rank {rank}: per-step wall ms {[round(x, 2) for x in step_wall]}; cgroup throttle (periods, usec) "
+              f"{cgroup_throttle()} <- {throttle0}; usable cores {usable_cores()}", file=sys.stderr, flush=True)
         print(f"[bench debug] rank {rank}: {ms / args.steps:.3f} ms/step; host time per step: submits {1e3 * dbg['submit_s'] / args.steps:.3f} ms, "
               f"flush {1e3 * dbg['flush_s'] / args.steps:.3f} ms", file=sys.stderr, flush=True)
     gpu_launches = agg.stats()["n_kernels"] - launches0  # every launch of the library's own kernels in the timed region

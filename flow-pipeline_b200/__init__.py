@@ -12,5 +12,5 @@ flow_pipeline_b200 shim module at the repository root.
 """
 from .flowagg import (  # noqa: F401
     FaConfig, FaMockerConfig, FlowAgg, FlowAggError, KEY_MODES, KEY_WORDS, ROW_DTYPE, HH_DTYPE,
-    build, lib_path, load_library, mocker_host,
+    build, lib_path, load_library, mocker_host, row_owner,
 )

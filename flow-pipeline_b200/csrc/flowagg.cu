@@ -911,6 +911,184 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
     return dropped ? FA_ERR_TABLE_FULL : FA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// merging aggregates: one context's rows into another's table; the box-wide exchange
+// ---------------------------------------------------------------------------------------------
+
+template <int KW>
+static cudaError_t launch_add_rows(fa_ctx *c, const fa_row *d_rows, unsigned long long n, uint32_t owner, uint32_t n_owners)
+{
+    SubmitParams p{};
+    fill_table_params(c, p);
+    const int grid = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->num_sms * 16);
+    k_add_rows<KW><<<grid, 256, 0, c->stream>>>(p, d_rows, n, owner, n_owners);
+    c->n_kernels++;
+    return cudaGetLastError();
+}
+
+static int add_rows_device(fa_ctx *c, const fa_row *d_rows, size_t n, uint32_t owner, uint32_t n_owners)
+{
+    if (!n) return FA_OK;
+    cudaError_t e;
+#define CALL_ADD(K) launch_add_rows<K>(c, d_rows, n, owner, n_owners)
+    FA_DISPATCH_KW(c->kw, CALL_ADD)
+#undef CALL_ADD
+    FA_CUDA(c, e);
+    return FA_OK;
+}
+
+extern "C" int fa_merge_rows(fa_ctx *c, const fa_row *rows, size_t n, uint32_t owner, uint32_t n_owners)
+{
+    if (!c || !c->d_slots || (n && !rows) || (n_owners > 1 && owner >= n_owners)) return FA_ERR_INVALID;
+    if (!n) return FA_OK;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaPointerAttributes attr{};
+    const bool on_device = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (on_device) {
+        if (attr.device != c->cfg.device) {  // a peer GPU's rows: read in place when the topology allows it
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->cfg.device, attr.device);
+            if (can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+                cudaGetLastError();
+            }
+            if (!can) {
+                fa_row *tmp = nullptr;
+                FA_CUDA(c, cudaMalloc(&tmp, n * sizeof(fa_row)));
+                cudaError_t ce = cudaMemcpyPeerAsync(tmp, c->cfg.device, rows, attr.device, n * sizeof(fa_row), c->stream);
+                int rc = ce == cudaSuccess ? add_rows_device(c, tmp, n, owner, n_owners) : FA_ERR_CUDA;
+                cudaStreamSynchronize(c->stream);
+                cudaFree(tmp);
+                FA_CUDA(c, ce);
+                return rc;
+            }
+        }
+        return add_rows_device(c, rows, n, owner, n_owners);
+    }
+    // host rows: through a device copy that lives until the kernel has read it
+    fa_row *tmp = nullptr;
+    FA_CUDA(c, cudaMalloc(&tmp, n * sizeof(fa_row)));
+    cudaError_t ce = cudaMemcpyAsync(tmp, rows, n * sizeof(fa_row), cudaMemcpyHostToDevice, c->stream);
+    int rc = ce == cudaSuccess ? add_rows_device(c, tmp, n, owner, n_owners) : FA_ERR_CUDA;
+    cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    FA_CUDA(c, ce);
+    return rc;
+}
+
+static int key_words_of_mode(int key_mode)
+{
+    switch (key_mode) {
+    case FA_KEY_FLOWS5M: return KeyTraits<FA_KEY_FLOWS5M>::KW;
+    case FA_KEY_ASPAIR: return KeyTraits<FA_KEY_ASPAIR>::KW;
+    case FA_KEY_SRCADDR: return KeyTraits<FA_KEY_SRCADDR>::KW;
+    case FA_KEY_DSTADDR: return KeyTraits<FA_KEY_DSTADDR>::KW;
+    case FA_KEY_5TUPLE: return KeyTraits<FA_KEY_5TUPLE>::KW;
+    case FA_KEY_SRCPORT: return KeyTraits<FA_KEY_SRCPORT>::KW;
+    case FA_KEY_DSTPORT: return KeyTraits<FA_KEY_DSTPORT>::KW;
+    default: return 0;
+    }
+}
+
+extern "C" int fa_row_owner(int key_mode, const fa_row *rows, size_t n, uint32_t n_owners, uint32_t *owner)
+{
+    const int kw = key_words_of_mode(key_mode);
+    if (!kw || !n_owners || (n && (!rows || !owner))) return FA_ERR_INVALID;
+    for (size_t i = 0; i < n; i++) {
+        unsigned long long h;
+        switch (kw) {
+        case 1: h = hash64<1>(rows[i].key); break;
+        case 2: h = hash64<2>(rows[i].key); break;
+        case 4: h = hash64<4>(rows[i].key); break;
+        default: h = hash64<11>(rows[i].key); break;
+        }
+        owner[i] = key_owner(h, n_owners);
+    }
+    return FA_OK;
+}
+
+static bool row_key_less(const fa_row &a, const fa_row &b, int kw)
+{
+    for (int k = 0; k < kw; k++)
+        if (a.key[k] != b.key[k]) return a.key[k] < b.key[k];
+    return false;
+}
+
+extern "C" int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
+{
+    if (!ctxs || n_ctx < 1 || !n || (flags & FA_FLUSH_KEEP)) return FA_ERR_INVALID;
+    for (int i = 0; i < n_ctx; i++)
+        if (!ctxs[i] || !ctxs[i]->d_slots || ctxs[i]->cfg.key_mode != ctxs[0]->cfg.key_mode) return FA_ERR_INVALID;
+    if (n_ctx == 1) return fa_flush(ctxs[0], rows, cap, n, flags);
+    // 1. every context: fold the replicas, compact its rows (unsorted) into its scratch block, empty its table
+    std::vector<uint64_t> groups(n_ctx, 0);
+    uint64_t dropped = 0;
+    for (int i = 0; i < n_ctx; i++) {
+        fa_ctx *c = ctxs[i];
+        FA_CUDA(c, cudaSetDevice(c->cfg.device));
+        int rc = merge_hot(c);
+        if (rc) return rc;
+        rc = read_counters(c);
+        if (rc) return rc;
+        groups[i] = c->h_counters->n_groups;
+        dropped += c->h_counters->n_dropped;
+        if (groups[i]) {
+            rc = ensure_scratch(c, groups[i] * sizeof(fa_row));
+            if (rc) return rc;
+            FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+            cudaError_t e;
+#define CALL_COMPACT(K) launch_compact<K>(c, (fa_row *)c->d_scratch, groups[i])
+            FA_DISPATCH_KW(c->kw, CALL_COMPACT)
+#undef CALL_COMPACT
+            FA_CUDA(c, e);
+        }
+        rc = reset_table(c);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n_ctx; i++) {
+        FA_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->cfg.device));
+        FA_CUDA(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));
+    }
+    // 2. the exchange: context j sums the rows it owns out of every context's compacted rows
+    for (int j = 0; j < n_ctx; j++)
+        for (int i = 0; i < n_ctx; i++) {
+            const int src = (i + j) % n_ctx;  // stagger the sources so that the peers are not all read in the same order
+            int rc = fa_merge_rows(ctxs[j], (const fa_row *)ctxs[src]->d_scratch, (size_t)groups[src], (uint32_t)j, (uint32_t)n_ctx);
+            if (rc) return rc;
+        }
+    uint64_t total = 0;
+    for (int j = 0; j < n_ctx; j++) {  // every reader is done before any scratch block is reused below
+        fa_ctx *c = ctxs[j];
+        FA_CUDA(c, cudaSetDevice(c->cfg.device));
+        int rc = read_counters(c);
+        if (rc) return rc;
+        total += c->h_counters->n_groups;
+        dropped += c->h_counters->n_dropped;
+    }
+    *n = (size_t)total;
+    if (total > cap || (total && !rows)) return FA_ERR_CAPACITY;
+    // 3. every context emits its share; the shares are disjoint, so the box order is a merge of sorted runs
+    std::vector<size_t> cut(1, 0);
+    size_t at = 0;
+    for (int j = 0; j < n_ctx; j++) {
+        size_t m = 0;
+        int rc = fa_flush(ctxs[j], rows + at, cap - at, &m, flags & FA_FLUSH_UNSORTED);
+        if (rc && rc != FA_ERR_TABLE_FULL) return rc;
+        at += m;
+        cut.push_back(at);
+    }
+    if (!(flags & FA_FLUSH_UNSORTED)) {
+        const int kw = ctxs[0]->kw;
+        auto less = [kw](const fa_row &a, const fa_row &b) { return row_key_less(a, b, kw); };
+        for (size_t width = 1; width < (size_t)n_ctx; width *= 2)  // pairwise merges of neighbouring runs
+            for (size_t j = 0; j + width < (size_t)n_ctx; j += 2 * width)
+                std::inplace_merge(rows + cut[j], rows + cut[j + width], rows + cut[std::min<size_t>(j + 2 * width, (size_t)n_ctx)], less);
+    }
+    return dropped ? FA_ERR_TABLE_FULL : FA_OK;
+}
+
 extern "C" int fa_reset(fa_ctx *c)
 {
     if (!c) return FA_ERR_INVALID;

@@ -120,10 +120,12 @@ __device__ __forceinline__ bool make_key(const Flow &f, uint32_t *key)
 
 // table / sketch hash; same arithmetic as the checker's restatement
 template <int KW>
-__device__ __forceinline__ unsigned long long hash64(const uint32_t *key)
+__host__ __device__ __forceinline__ unsigned long long hash64(const uint32_t *key)
 {
     unsigned long long h = 0x243F6A8885A308D3ull;
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int i = 0; i < KW; i += 2) {
         unsigned long long w = key[i];
         if (i + 1 < KW) w |= (unsigned long long)key[i + 1] << 32;
@@ -804,6 +806,27 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsi
         r.packets = v[1];
         r.count = v[2];
         rows[at] = r;
+    }
+}
+
+// Which of n_owners contexts merges a key in a box-wide roll-up.  The table index uses hi32(h), this uses lo32(h).
+__host__ __device__ __forceinline__ uint32_t key_owner(unsigned long long h, uint32_t n_owners) { return (uint32_t)h % n_owners; }
+
+// SummingMergeTree's merge step (create.sh:88-90) for rows that are already aggregates: another context's
+// flush output, possibly read straight from a peer GPU's memory over NVLink.  n_owners > 1 keeps only the
+// rows this context owns (the hash-partitioned exchange of fa_flush_box): the key is read first and the values
+// only for owned rows.
+template <int KW>
+__global__ void __launch_bounds__(256) k_add_rows(const SubmitParams p, const fa_row *rows, unsigned long long n, uint32_t owner,
+                                                  uint32_t n_owners)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t key[KW];
+#pragma unroll
+        for (int k = 0; k < KW; k++) key[k] = rows[i].key[k];
+        const unsigned long long h = hash64<KW>(key);
+        if (n_owners > 1u && key_owner(h, n_owners) != owner) continue;
+        table_add<KW>(p, key, h, rows[i].bytes, rows[i].packets, rows[i].count);
     }
 }
 

@@ -95,6 +95,9 @@ _PROTOS = {
     "fa_sync": (C.c_int, [C.c_void_p]),
     "fa_stats_get": (C.c_int, [C.c_void_p, C.POINTER(FaStats)]),
     "fa_flush": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32]),
+    "fa_merge_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
+    "fa_row_owner": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "fa_flush_box": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32]),
     "fa_reset": (C.c_int, [C.c_void_p]),
     "fa_cms_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fa_cms_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
@@ -146,6 +149,18 @@ def mocker_host(cfg: FaMockerConfig, first: int, n: int):
     if rc:
         raise FlowAggError(rc, "fa_mocker_host")
     return buf[: need.value], offs
+
+
+def row_owner(key_mode, rows, n_owners):
+    """Owner in [0, n_owners) of every row's key: the hash partition of the box-wide exchange (fa_row_owner)."""
+    L = load_library()
+    mode = KEY_MODES[key_mode] if isinstance(key_mode, str) else int(key_mode)
+    rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+    out = np.zeros(len(rows), dtype=np.uint32)
+    rc = L.fa_row_owner(mode, rows.ctypes.data, len(rows), n_owners, out.ctypes.data)
+    if rc:
+        raise FlowAggError(rc, "fa_row_owner")
+    return out
 
 
 def _ptr(x):
@@ -254,6 +269,34 @@ class FlowAgg:
                 continue
             self._check(rc, "fa_flush", ok)
             self._rows_cap = max(len(rows), 1 << 16)
+            return rows[: n.value]
+
+    def merge_rows(self, rows, n=None, owner=0, n_owners=1):
+        """SummingMergeTree's merge (create.sh:88-90): add rows that are already aggregates (another context's or an
+        earlier window's flush output).  rows: a ROW_DTYPE array, or a device tensor / address with n rows.
+        n_owners > 1: only the rows whose key this context owns (row_owner(...) == owner)."""
+        if isinstance(rows, np.ndarray):
+            rows = np.ascontiguousarray(rows, dtype=ROW_DTYPE)
+            n = len(rows)
+        self._check(self._L.fa_merge_rows(self._h, _ptr(rows), int(n), owner, n_owners), "fa_merge_rows")
+
+    @staticmethod
+    def flush_box(ctxs, sort=True, allow_full=False):
+        """Exact roll-up over every context of the box (one per GPU): hash-partitioned exchange over peer memory,
+        then every context's share, in ORDER BY order.  Resets every context."""
+        L = load_library()
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        flags = 0 if sort else FA_FLUSH_UNSORTED
+        n = C.c_size_t()
+        cap = 1 << 16
+        while True:
+            rows = np.empty(cap, dtype=ROW_DTYPE)
+            rc = L.fa_flush_box(arr, len(ctxs), rows.ctypes.data, len(rows), C.byref(n), flags)
+            if rc == -4 and n.value > len(rows):
+                cap = n.value
+                continue
+            if rc and not (allow_full and rc == -5):
+                raise FlowAggError(rc, "fa_flush_box", "; ".join(L.fa_last_error(c._h).decode() for c in ctxs))
             return rows[: n.value]
 
     def reset(self):

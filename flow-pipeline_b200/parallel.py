@@ -100,6 +100,55 @@ def merge_rows(rows: np.ndarray, key_words: int, group=None, device="cpu"):
     return sum_rows_by_key(rows, key_words)
 
 
+def partition_rows(rows: np.ndarray, key_mode, world: int):
+    """Rows grouped by owner rank (fa_row_owner's hash partition) and the per-owner counts."""
+    from .flowagg import row_owner
+
+    owner = row_owner(key_mode, rows, world)
+    order = np.argsort(owner, kind="stable")
+    return rows[order], np.bincount(owner, minlength=world).astype(np.int64)
+
+
+def exchange_partial_rows(rows: np.ndarray, key_mode, group=None, device="cpu"):
+    """All-to-all of partial roll-up rows by key owner.  Returns the rows this rank owns, one partial per sender,
+    as an int64 tensor [n, words] on `device` (view it as ROW_DTYPE on the host)."""
+    world = dist.get_world_size(group)
+    rows, counts = partition_rows(rows, key_mode, world)
+    words = ROW_DTYPE.itemsize // 8
+    send_counts = torch.from_numpy(counts).to(device)
+    recv_counts = torch.zeros_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    rc = [int(x) for x in recv_counts.cpu().tolist()]
+    sc = [int(x) for x in counts.tolist()]
+    send = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64).reshape(len(rows), words).copy()).to(device)
+    recv = torch.empty((sum(rc), words), dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=group)
+    return recv
+
+
+def rows_of_tensor(t: torch.Tensor) -> np.ndarray:
+    return np.ascontiguousarray(t.cpu().numpy()).view(ROW_DTYPE).reshape(-1)
+
+
+def exchange_rows(agg: FlowAgg, group=None, device="cpu"):
+    """The one exchange step of an exact box-wide roll-up when every rank is its own process:
+    each rank flushes its partial rows, sends every row to the rank that owns its key (all-to-all; NCCL
+    send/recv over NVLink when `device` is a CUDA device), folds what it receives into its own table on the GPU
+    (fa_merge_rows) and flushes again.  Returns this rank's share: the exact, fully merged rows of the keys it
+    owns, in ORDER BY order.  The shares of different ranks are disjoint."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return agg.flush()
+    recv = exchange_partial_rows(agg.flush(sort=False), agg.key_mode, group, device)
+    if recv.is_cuda:
+        torch.cuda.current_stream(recv.device).synchronize()
+        agg.merge_rows(recv, n=recv.shape[0])  # straight from device memory
+        agg.sync()
+    else:
+        agg.merge_rows(rows_of_tensor(recv))
+    return agg.flush()
+
+
 def sum_rows_by_key(rows: np.ndarray, key_words: int):
     if len(rows) == 0:
         return rows

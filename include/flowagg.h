@@ -173,6 +173,26 @@ int fa_stats_get(fa_ctx *ctx, fa_stats *out); /* implies fa_sync */
  * group table (not the sketch).  *n = rows available; FA_ERR_CAPACITY if
  * cap < *n (nothing is reset then). */
 int fa_flush(fa_ctx *ctx, fa_row *rows, size_t cap, size_t *n, uint32_t flags);
+
+/* The merge step of the SummingMergeTree behind flows_5m (compose/clickhouse/create.sh:88-90: rows with equal
+ * ORDER BY keys are summed) for rows that are already aggregates -- an earlier window's or another context's
+ * fa_flush output.  `rows` may be host or device memory (a peer GPU's included).  n_owners > 1 adds only the rows
+ * whose key this context owns (fa_row_owner(...) == owner); n_owners <= 1 adds all.  Asynchronous on the
+ * context's stream for device rows; host rows are copied before the call returns. */
+int fa_merge_rows(fa_ctx *ctx, const fa_row *rows, size_t n, uint32_t owner, uint32_t n_owners);
+
+/* owner[i] in [0, n_owners) of rows[i] (host memory) under `key_mode`: the hash partition fa_flush_box and a
+ * one-process-per-GPU host use for the exchange step of an exact box-wide roll-up.  Pure host function. */
+int fa_row_owner(int key_mode, const fa_row *rows, size_t n, uint32_t n_owners, uint32_t *owner);
+
+/* Exact box-wide roll-up of n_ctx contexts (same key mode; normally one per GPU of the box = one per Kafka partition
+ * group, inserter/inserter.go:176).  Kafka does not partition by group key, so every context holds partial sums of
+ * the same keys: one hash-partitioned exchange (context j pulls the rows it owns out of every context's compacted
+ * rows -- peer loads over NVLink when the devices allow it, a peer copy otherwise -- and sums them in its own
+ * table), then every context emits its share.  rows: host array, canonical order unless FA_FLUSH_UNSORTED.
+ * Every context is reset.  FA_ERR_CAPACITY: *n = rows needed; the contexts then hold the exchanged (disjoint)
+ * roll-ups and the call can be repeated with a larger array.  FA_FLUSH_KEEP is not supported (FA_ERR_INVALID). */
+int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t cap, size_t *n, uint32_t flags);
 int fa_reset(fa_ctx *ctx); /* clear table, sketch and statistics */
 
 /* Date column of a FLOWS5M row: toDate(TimeReceived), days since epoch. */

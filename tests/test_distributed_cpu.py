@@ -46,8 +46,14 @@ def _worker(rank, world, port, q):
     top_local = o.topk(g, d, wl, 4, cands, k).view(fp.HH_DTYPE)
     top = par.merge_topk(top_local, k, 4)
     rows = par.merge_rows(np.concatenate(rows_all), 4)
+    # hash-partitioned exchange (the high-cardinality merge): every rank ends up with the partials of the keys it owns
+    part = par.sum_rows_by_key(np.concatenate(cand_all), 4)
+    got = par.rows_of_tensor(par.exchange_partial_rows(part, "srcaddr"))
+    assert (fp.row_owner("srcaddr", got, world) == rank).all()
+    share = par.sum_rows_by_key(got, 4)
+    q.put(("share", rank, share.copy()))
     if rank == 0:
-        q.put((g.copy(), top.copy(), rows.copy()))
+        q.put(("main", g.copy(), top.copy(), rows.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,7 +69,14 @@ def test_world2_gloo_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    g, top, rows = q.get(timeout=120)
+    shares, main = {}, None
+    while len(shares) < 2 or main is None:
+        item = q.get(timeout=120)
+        if item[0] == "share":
+            shares[item[1]] = item[2]
+        else:
+            main = item[1:]
+    g, top, rows = main
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -76,3 +89,9 @@ def test_world2_gloo_matches_single_process():
     want_top = o.topk(cms, 4, 10, 4, cand, 20)
     assert np.array_equal(top["key"], want_top["key"]) and np.array_equal(top["estimate"], want_top["estimate"])
     assert np.array_equal(rows, want_rows)
+    # the two shares are disjoint, both non-trivial, and together they are the exact group-by of everything
+    import importlib
+
+    par = importlib.import_module("flow-pipeline_b200.parallel")
+    assert len(shares[0]) and len(shares[1]) and len(shares[0]) + len(shares[1]) == len(cand)
+    assert np.array_equal(par.sum_rows_by_key(np.concatenate([shares[0], shares[1]]), 4), cand)

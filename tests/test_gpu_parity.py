@@ -454,9 +454,13 @@ def _nccl_worker(rank, world, port, q):
             b.submit(buf, offs)
         top = par.box_topk(a, 100)                        # NCCL all-reduce of the sketches + merge
         top2 = par.box_topk(a, 100)                       # a second query must not double count
-        rows = par.merge_rows(b.flush(), 4, device=torch.device("cuda", rank))
+        rows = par.merge_rows(b.flush(keep=True), 4, device=torch.device("cuda", rank))
+        # the same roll-up through the hash-partitioned exchange: all-to-all over NCCL, merged on the GPU
+        share = par.exchange_rows(b, device=torch.device("cuda", rank))
+        assert (fp.row_owner("flows5m", share, world) == rank).all()
+    q.put(("share", rank, share.copy()))
     if rank == 0:
-        q.put((top.copy(), top2.copy(), rows.copy()))
+        q.put(("main", top.copy(), top2.copy(), rows.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -474,7 +478,14 @@ def test_one_process_per_gpu_box_topk_and_row_merge_over_nccl(fp, oracle, torch_
     procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    top, top2, rows = q.get(timeout=300)
+    shares, main = {}, None
+    while len(shares) < 2 or main is None:
+        item = q.get(timeout=300)
+        if item[0] == "share":
+            shares[item[1]] = item[2]
+        else:
+            main = item[1:]
+    top, top2, rows = main
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -486,6 +497,10 @@ def test_one_process_per_gpu_box_topk_and_row_merge_over_nccl(fp, oracle, torch_
         assert np.array_equal(t["key"], want["key"]) and np.array_equal(t["estimate"], want["estimate"])
     want_rows, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
     assert np.array_equal(rows, want_rows)
+    both = np.concatenate([shares[0], shares[1]])
+    assert len(both) == len(want_rows)
+    order = np.lexsort(tuple(both["key"][:, i] for i in reversed(range(4))))
+    assert np.array_equal(both[order], want_rows)
 
 
 def _random_wire_messages(seed, n):
@@ -652,3 +667,76 @@ def test_record_to_lane_stride_is_result_neutral(torch_cuda, stride, first):
         env["FA_LANE_STRIDE"] = stride
     r = subprocess.run([sys.executable, "-c", _STRIDE_SNIPPET.format(root=root, first=first)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def _all_ones_port_records(n):
+    """SrcPort = 0xFFFFFFFF (a legal uint32): the one key that equals the table's empty marker."""
+    return [b"\x48" + bytes([1 + i % 100]) + b"\x50\x02" + b"\xa8\x01\xff\xff\xff\xff\x0f" for i in range(n)]
+
+
+@pytest.mark.parametrize("mode", ["aspair", "srcaddr", "5tuple", "srcport", "flows5m"])
+def test_merge_rows_is_the_summing_merge(fp, oracle, torch_cuda, mode):
+    """fa_merge_rows: rows that are already aggregates are summed into the table by key (SummingMergeTree,
+    create.sh:88-90) -- from host memory, from device memory, and filtered by key owner."""
+    cfg = fp.FaMockerConfig.make(seed=17, flows_per_second=40, n_src_as=32, n_dst_as=32, addr_mode=1, framed=True)
+    n = 60_000
+    buf, offs = fp.mocker_host(cfg, 0, n)
+    extra = frame(_all_ones_port_records(7)) if mode == "srcport" else []
+    if extra:
+        eb, eo = concat_records(extra)
+        buf = np.concatenate([buf[: offs[n]], eb])
+        offs = np.concatenate([offs, (eo[1:] + offs[n]).astype(np.uint32)])
+    total = len(offs) - 1
+    half = total // 2
+    want, _, _ = oracle.run_batch(buf, offs, key_mode=mode)
+    lo = (buf[: offs[half]], offs[: half + 1])
+    hi = (buf[offs[half]: offs[total]], (offs[half:] - offs[half]).astype(np.uint32))
+    with fp.FlowAgg(mode, table_capacity=1 << 18) as a, fp.FlowAgg(mode, table_capacity=1 << 18) as b:
+        a.submit(*lo)
+        b.submit(*hi)
+        part = a.flush(sort=False)
+        b.merge_rows(part)                                   # host rows
+        assert np.array_equal(b.flush(keep=True), want)
+        # again from device memory, split over three "owners": every row lands exactly once
+        b.reset()
+        b.submit(*hi)
+        d_rows = torch_cuda.from_numpy(part.view(np.int64).reshape(len(part), -1).copy()).cuda()
+        for owner in range(3):
+            b.merge_rows(d_rows, n=len(part), owner=owner, n_owners=3)
+        b.sync()
+        assert np.array_equal(b.flush(), want)
+        owners = fp.row_owner(mode, part, 3)
+        assert set(np.unique(owners)) <= {0, 1, 2} and (len(part) < 30 or len(np.unique(owners)) == 3)
+
+
+@pytest.mark.parametrize("mode", ["flows5m", "5tuple", "srcport"])
+def test_flush_box_is_the_exact_group_by_of_every_context(fp, oracle, torch_cuda, mode):
+    """fa_flush_box: contexts that saw different partitions hold partial sums of the same keys; the hash-partitioned
+    exchange (peer loads across GPUs when the box has several) leaves the exact roll-up of everything, in
+    ORDER BY order, and empty contexts."""
+    n_dev = torch_cuda.cuda.device_count()
+    n_ctx = max(3, min(n_dev, 4))
+    cfg = fp.FaMockerConfig.make(seed=23, flows_per_second=30, n_src_as=16, n_dst_as=16, addr_mode=1, framed=True)
+    per = 30_000
+    buf, offs = fp.mocker_host(cfg, 0, n_ctx * per)
+    if mode == "srcport":
+        eb, eo = concat_records(frame(_all_ones_port_records(5)))
+        buf = np.concatenate([buf[: offs[-1]], eb])
+        offs = np.concatenate([offs, (eo[1:] + offs[-1]).astype(np.uint32)])
+    want, _, _ = oracle.run_batch(buf, offs, key_mode=mode)
+    ctxs = [fp.FlowAgg(mode, device=i % n_dev, table_capacity=1 << 18) for i in range(n_ctx)]
+    try:
+        total = len(offs) - 1
+        cuts = [min(i * per, total) for i in range(n_ctx)] + [total]
+        for i, c in enumerate(ctxs):
+            a, b = cuts[i], cuts[i + 1]
+            c.submit(buf[offs[a]: offs[b]], (offs[a: b + 1] - offs[a]).astype(np.uint32))
+        rows = fp.FlowAgg.flush_box(ctxs)
+        assert np.array_equal(rows, want)
+        assert all(len(c.flush()) == 0 for c in ctxs)         # every context was reset
+        ctxs[0].submit(buf[: offs[100]], offs[:101])           # and is usable again
+        w2, _, _ = oracle.run_batch(buf[: offs[100]], offs[:101], key_mode=mode)
+        assert np.array_equal(fp.FlowAgg.flush_box(ctxs), w2)
+    finally:
+        for c in ctxs:
+            c.close()
