@@ -66,6 +66,7 @@ struct Flags {
     int Devices = 1;                      // -gpus: partition p runs on GPU p mod gpus
     std::string Sink = "flows5m";         // -sink flows5m: roll-up rows (create.sh:70-87); rows: the inserter's own
                                           //       14-column row per flow (inserter.go:51-66,142-157)
+    bool FlushBox = false;                // -flush.box: the closing flush is ONE exact roll-up over every partition (fa_flush_box)
     bool DryRun = false;                  // -dry-run: walk the claims and fill slabs, no GPU, no aggregates
     bool Metrics = false;                 // -metrics: serve -metrics.addr (off by default in this mirror)
 };
@@ -128,6 +129,7 @@ static bool parse_flags(int argc, char **argv, Flags &f)
         else if (a == "sink") f.Sink = val();
         else if (a == "gpus") f.Devices = atoi(val().c_str());
         else if (a == "dry-run") f.DryRun = true;
+        else if (a == "flush.box") f.FlushBox = true;
         else if (a == "metrics") f.Metrics = true;
         else {
             fprintf(stderr, "flag provided but not defined: -%s\n", a.c_str());
@@ -380,11 +382,12 @@ struct state {
     }
 
     // (*state).flush, inserter.go:90-111: rows out, table reset
-    bool flush(PartitionState &ps, ConsumerGroupSession &sess)
+    bool flush(PartitionState &ps, ConsumerGroupSession &sess, bool closing = false)
     {
         logf(2, "Processed %ld records in the last iteration.", msgCount.exchange(0));
         submit_slab(ps, sess);
         if (fl.DryRun || fl.Sink == "rows") return true;
+        if (closing && fl.FlushBox) return true;  // main() merges every partition's table in one fa_flush_box
         size_t n = 0;
         std::vector<fa_row> rows(1 << 16);
         int rc = fa_flush(ps.ctx, rows.data(), rows.size(), &n, 0);
@@ -476,8 +479,38 @@ struct state {
                 deadline = std::chrono::steady_clock::now() + std::chrono::duration<double>(fl.FlushTime);
             }
         }
-        flush(ps, sess);
+        flush(ps, sess, true);
         return 0;
+    }
+
+    // -flush.box: Kafka does not partition by group key, so the partitions hold partial sums of the same keys.
+    // A SummingMergeTree would merge the partial rows later (create.sh:88-90); this emits them merged already.
+    void flush_box(std::vector<PartitionState> &parts)
+    {
+        std::vector<fa_ctx *> ctxs;
+        for (auto &ps : parts)
+            if (ps.ctx) ctxs.push_back(ps.ctx);
+        if (ctxs.empty()) return;
+        size_t n = 0;
+        std::vector<fa_row> rows(1 << 16);
+        int rc = fa_flush_box(ctxs.data(), (int)ctxs.size(), rows.data(), rows.size(), &n, 0);
+        if (rc == FA_ERR_CAPACITY) {
+            rows.resize(n);
+            rc = fa_flush_box(ctxs.data(), (int)ctxs.size(), rows.data(), rows.size(), &n, 0);
+        }
+        if (rc && rc != FA_ERR_TABLE_FULL) {
+            logf(0, "fa_flush_box: %s (%s)", fa_strerror(rc), fa_last_error(ctxs[0]));
+            exit(1);
+        }
+        bad = 0;
+        for (fa_ctx *c : ctxs) {
+            fa_stats st;
+            fa_stats_get(c, &st);
+            bad += st.n_bad;
+        }
+        for (size_t i = 0; i < n; i++) write_row(rows[i]);
+        fflush(out);
+        rows_written += n;
     }
 };
 
@@ -561,6 +594,7 @@ int main(int argc, char **argv)
     std::vector<std::thread> th;
     for (size_t p = 0; p < np; p++) th.emplace_back([&, p] { s.ConsumeClaim(sess, *claims[p], parts[p]); });
     for (auto &t : th) t.join();
+    if (s.fl.FlushBox && !s.fl.DryRun && s.fl.Sink != "rows") s.flush_box(parts);
     s.Cleanup(sess);
     uint64_t total = 0;
     for (auto &kv : sess.marked) total += (uint64_t)kv.second;

@@ -385,6 +385,17 @@ def test_host_inserter_mirror_rows_equal_oracle(fp, oracle, torch_cuda, tmp_path
             ts = time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(w["key"][0])))
             want.append((str(w["key"][1]), str(w["key"][2]), f"[{w['key'][3]}]", str(w["bytes"]), str(w["packets"]), str(w["count"]), ts))
     assert got == sorted(want)
+    # -flush.box: the closing flush is one exact roll-up over both partitions, already in ORDER BY order
+    buf, offs = fp.mocker_host(cfg, 0, 40000)
+    merged, _, _ = oracle.run_batch(buf, offs, key_mode="flows5m")
+    out2 = tmp_path / "rows_box.tsv"
+    r = subprocess.run([exe, "-claim.file", ",".join(files), "-flush.count", "0", "-flush.dur", "1h", "-flush.box", "-out", str(out2)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got2 = [tuple(l.split("\t")[1:5] + l.split("\t")[8:11]) for l in out2.read_text().splitlines()]
+    want2 = [(time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(w["key"][0]))), str(w["key"][1]), str(w["key"][2]), f"[{w['key'][3]}]",
+              str(w["bytes"]), str(w["packets"]), str(w["count"])) for w in merged]
+    assert got2 == want2
 
 
 @pytest.mark.parametrize("mode,addr_mode,cms", [("flows5m", 0, False), ("aspair", 0, False), ("srcaddr", 1, True), ("dstport", 0, False)])
