@@ -130,6 +130,25 @@ func (ps *partitionState) flush(session sarama.ConsumerGroupSession, sink func(r
 	sink(rows[:n])
 }
 
+// flushBox is the box-wide variant: Kafka does not partition by group key, so the partitions' tables hold
+// partial sums of the same keys.  fa_flush_box exchanges them by key owner between the GPUs and returns
+// each key once, in ORDER BY order (what the SummingMergeTree would converge to, create.sh:88-90).
+// Call it with every live partitionState's ctx from one goroutine while the claims are quiescent
+// (e.g. from Cleanup, inserter.go:172).
+func flushBox(ctxs []*C.fa_ctx, sink func(rows []C.fa_row)) {
+	rows := make([]C.fa_row, 1<<16)
+	var n C.size_t
+	rc := C.fa_flush_box(&ctxs[0], C.int(len(ctxs)), &rows[0], C.size_t(len(rows)), &n, 0)
+	if rc == C.FA_ERR_CAPACITY {
+		rows = make([]C.fa_row, n)
+		rc = C.fa_flush_box(&ctxs[0], C.int(len(ctxs)), &rows[0], n, &n, 0)
+	}
+	if rc != C.FA_OK && rc != C.FA_ERR_TABLE_FULL {
+		log.Fatalf("fa_flush_box: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ctxs[0])))
+	}
+	sink(rows[:n])
+}
+
 // ConsumeClaim replaces (*state).ConsumeClaim (inserter.go:176-196); sarama calls it once per
 // claimed partition, each with its own fa_ctx: no cross-goroutine lock.
 func (s *state) ConsumeClaimB200(session sarama.ConsumerGroupSession, claim sarama.ConsumerGroupClaim) error {
