@@ -22,7 +22,61 @@
 #pragma once
 #include <stdint.h>
 
+// The decoder also compiles as plain host C++ (nvcc's host pass): tests/decode_host builds it that way so the
+// CPU test suite can drive the very same template against the oracle and the golden vectors.  That build is test
+// infrastructure; nothing in the product calls the host instantiation.
+#define FA_DEV __host__ __device__
+#ifdef __CUDA_ARCH__
+#define FA_UNROLL _Pragma("unroll")
+#else
+#define FA_UNROLL
+#endif
+
 namespace fa {
+
+FA_DEV __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+FA_DEV __forceinline__ uint32_t byte_swap(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
+#endif
+}
+FA_DEV __forceinline__ uint32_t find_first_set(uint32_t x)  // 1-based, 0 for x == 0
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)x);
+#else
+    return (uint32_t)__builtin_ffs((int)x);
+#endif
+}
+FA_DEV __forceinline__ uint32_t shl_clamp(uint32_t n)  // 1 << n, 0 for n >= 32 (shl.b32 clamps)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t bit;
+    asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(n));
+    return bit;
+#else
+    return n < 32u ? 1u << n : 0u;
+#endif
+}
+FA_DEV __forceinline__ uint32_t load_word(const uint32_t *p)
+{
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // which fields a kernel needs; everything else is skipped and its code removed
 enum : uint32_t {
@@ -59,17 +113,18 @@ struct Flow {
 struct ByteSrc {
     const uint32_t *words;
     uint32_t limit_word;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return __ldg(words + (i < limit_word ? i : limit_word)); }
-    __device__ __forceinline__ uint32_t byte(uint32_t pos) const { return (word(pos >> 2) >> ((pos & 3u) * 8u)) & 0xffu; }
-    __device__ __forceinline__ void window(uint32_t pos, uint32_t &lo, uint32_t &hi) const
+    FA_DEV __forceinline__ uint32_t word(uint32_t i) const { return load_word(words + (i < limit_word ? i : limit_word)); }
+    FA_DEV __forceinline__ uint32_t byte(uint32_t pos) const { return (word(pos >> 2) >> ((pos & 3u) * 8u)) & 0xffu; }
+    FA_DEV __forceinline__ void window(uint32_t pos, uint32_t &lo, uint32_t &hi) const
     {
         const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
         const uint32_t a = word(i), b = word(i + 1), c = word(i + 2);
-        lo = __funnelshift_r(a, b, sh);
-        hi = __funnelshift_r(b, c, sh);
+        lo = funnel_r(a, b, sh);
+        hi = funnel_r(b, c, sh);
     }
 };
 
+#ifdef __CUDACC__
 // Byte source over a tile resident in (padded) SHARED memory, addressed by its
 // 32-bit shared-window address so the loads are LDS, never generic.
 struct SmemSrc {
@@ -94,10 +149,11 @@ struct SmemSrc {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
         asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
         asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
-        lo = __funnelshift_r(w0, w1, sh);
-        hi = __funnelshift_r(w1, w2, sh);
+        lo = funnel_r(w0, w1, sh);
+        hi = funnel_r(w1, w2, sh);
     }
 };
+#endif  // __CUDACC__
 
 // ---- slow paths (out of line, everything by value) -----------------------------
 
@@ -108,7 +164,7 @@ struct VarintRes {
 
 // protowire.ConsumeVarint, byte at a time
 template <class Src>
-__device__ __noinline__ VarintRes varint_slow(const Src s, uint32_t pos, uint32_t end)
+FA_DEV __noinline__ VarintRes varint_slow(const Src s, uint32_t pos, uint32_t end)
 {
     VarintRes r;
     r.v = 0;
@@ -134,7 +190,7 @@ __device__ __noinline__ VarintRes varint_slow(const Src s, uint32_t pos, uint32_
 }
 
 template <class Src>
-__device__ __noinline__ bool utf8_valid(const Src s, uint32_t pos, uint32_t n)
+FA_DEV __noinline__ bool utf8_valid(const Src s, uint32_t pos, uint32_t n)
 {
     uint32_t i = 0;
     while (i < n) {
@@ -168,7 +224,7 @@ __device__ __noinline__ bool utf8_valid(const Src s, uint32_t pos, uint32_t n)
 // protowire.ConsumeFieldValue(StartGroupType): returns the position after the
 // matching end-group tag, or 0xFFFFFFFF on error.
 template <class Src>
-__device__ __noinline__ uint32_t skip_group(const Src s, uint32_t pos, uint32_t end, uint32_t start_num)
+FA_DEV __noinline__ uint32_t skip_group(const Src s, uint32_t pos, uint32_t end, uint32_t start_num)
 {
     uint32_t stack[FA_MAX_GROUP_DEPTH];
     int depth = 0;
@@ -221,7 +277,7 @@ __device__ __noinline__ uint32_t skip_group(const Src s, uint32_t pos, uint32_t 
 // ---- field stores: predicated selects, no branches ----------------------------------
 
 template <uint32_t NEED>
-__device__ __forceinline__ void store_varint_field(Flow &f, const uint32_t num, const unsigned long long v)
+FA_DEV __forceinline__ void store_varint_field(Flow &f, const uint32_t num, const unsigned long long v)
 {
     // consumeUint64 / consumeUint32 / consumeEnum: last value wins, u32 = low 32 bits
     const uint32_t v32 = (uint32_t)v;
@@ -242,17 +298,17 @@ __device__ __forceinline__ void store_varint_field(Flow &f, const uint32_t num, 
 
 // first min(len,16) payload bytes -> 4 big-endian words, zero right-padded
 template <class Src>
-__device__ __forceinline__ void load_addr(const Src s, uint32_t pos, uint32_t len, uint32_t out[4])
+FA_DEV __forceinline__ void load_addr(const Src s, uint32_t pos, uint32_t len, uint32_t out[4])
 {
     const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
     uint32_t w[5];
-#pragma unroll
+FA_UNROLL
     for (int k = 0; k < 5; k++) w[k] = s.word(i + k);
     const uint32_t n = len < 16u ? len : 16u;
-#pragma unroll
+FA_UNROLL
     for (int k = 0; k < 4; k++) {
-        const uint32_t le = __funnelshift_r(w[k], w[k + 1], sh);
-        const uint32_t be = __byte_perm(le, 0, 0x0123);
+        const uint32_t le = funnel_r(w[k], w[k + 1], sh);
+        const uint32_t be = byte_swap(le);
         const int nb = (int)n - 4 * k;  // valid bytes in this word
         const uint32_t mask = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : (0xFFFFFFFFu << (32 - 8 * nb)));
         out[k] = be & mask;
@@ -270,16 +326,16 @@ __host__ __device__ constexpr uint32_t need_mask_lo(uint32_t need)
 __host__ __device__ constexpr uint32_t need_mask_hi(uint32_t need) { return (need & F_TIME_FLOW_START) ? 1u << (38 - 32) : 0u; }
 
 template <uint32_t NEED>
-__device__ __forceinline__ bool varint_field_needed(uint32_t num)
+FA_DEV __forceinline__ bool varint_field_needed(uint32_t num)
 {
     constexpr uint32_t M0 = need_mask_lo(NEED), M1 = need_mask_hi(NEED);
     // shl.b32 clamps: a shift of 32 or more yields 0, so out-of-range numbers are "not needed"
     uint32_t bit;
-    asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(num));
+    bit = shl_clamp(num);
     bool need = (bit & M0) != 0u;
     if (M1 != 0u) {
         uint32_t bit1;
-        asm("shl.b32 %0, 1, %1;" : "=r"(bit1) : "r"(num - 32u));  // num < 32 wraps to a huge shift: 0
+        bit1 = shl_clamp(num - 32u);  // num < 32 wraps to a huge shift: 0
         need = need || (bit1 & M1) != 0u;
     }
     return need;
@@ -288,7 +344,7 @@ __device__ __forceinline__ bool varint_field_needed(uint32_t num)
 // everything that is neither a varint nor length-delimited: fixed32/fixed64 skips, group skips,
 // and the error cases.  Returns the new position, 0xFFFFFFFF on error.
 template <class Src>
-__device__ __noinline__ uint32_t skip_other(const Src s, uint32_t pos, uint32_t end, uint32_t wt, uint32_t num)
+FA_DEV __noinline__ uint32_t skip_other(const Src s, uint32_t pos, uint32_t end, uint32_t wt, uint32_t num)
 {
     if (pos > end) return 0xFFFFFFFFu;
     if (wt == 5) return end - pos < 4 ? 0xFFFFFFFFu : pos + 4;
@@ -307,7 +363,7 @@ __device__ __noinline__ uint32_t skip_other(const Src s, uint32_t pos, uint32_t 
 // loop ends exactly on `end`.  Values written by a record that is then rejected are
 // never looked at.
 template <uint32_t NEED, class Src>
-__device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const uint32_t end, Flow &f)
+FA_DEV __forceinline__ bool decode_message(const Src s, uint32_t pos, const uint32_t end, Flow &f)
 {
     uint32_t min_num = 1u;  // smallest field number seen: 0 is illegal; checked once, after the loop
     while (pos < end) {
@@ -319,7 +375,7 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
             wt = lo & 7u;
             num = (lo >> 3) & 0xfu;
             pos += 1u;
-            xlo = __funnelshift_r(lo, hi, 8);
+            xlo = funnel_r(lo, hi, 8);
             xhi = hi >> 8;
         } else if (!(lo & 0x8000u)) {
             // 2-byte tag: fields 16..2047
@@ -327,7 +383,7 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
             wt = tag & 7u;
             num = tag >> 3;
             pos += 2u;
-            xlo = __funnelshift_r(lo, hi, 16);
+            xlo = funnel_r(lo, hi, 16);
             xhi = hi >> 16;
         } else {
             // three bytes or more: field numbers >= 2048 or an over-long encoding (rare)
@@ -348,7 +404,7 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
             const uint32_t stop = ~xlo & 0x80808080u;  // terminator bytes among the first four
             if (__builtin_expect(stop != 0u, 1)) {
                 // 1..4 bytes
-                const uint32_t t = __ffs(stop);  // 8,16,24,32
+                const uint32_t t = find_first_set(stop);  // 8,16,24,32
                 pos += t >> 3;
                 if (varint_field_needed<NEED>(num)) {
                     const uint32_t x = xlo & (0xFFFFFFFFu >> ((32u - t) & 31u));
@@ -412,7 +468,7 @@ __device__ __forceinline__ bool decode_message(const Src s, uint32_t pos, const 
 // Decode the record occupying [pos,end): bare message, or varint(len) || message
 // whose length must fill the span exactly.
 template <uint32_t NEED, class Src>
-__device__ __forceinline__ bool decode_record(const Src s, uint32_t pos, uint32_t end, bool framed, Flow &f)
+FA_DEV __forceinline__ bool decode_record(const Src s, uint32_t pos, uint32_t end, bool framed, Flow &f)
 {
     if (framed) {
         if (pos >= end) return false;
@@ -436,11 +492,11 @@ __device__ __forceinline__ bool decode_record(const Src s, uint32_t pos, uint32_
     return decode_message<NEED>(s, pos, end, f);
 }
 
-__device__ __forceinline__ void flow_reset(Flow &f)
+FA_DEV __forceinline__ void flow_reset(Flow &f)
 {
     f.time_received = f.sampling_rate = f.time_flow_start = f.bytes = f.packets = 0;
     f.type = f.sequence_num = f.src_as = f.dst_as = f.etype = f.proto = f.src_port = f.dst_port = 0;
-#pragma unroll
+FA_UNROLL
     for (int i = 0; i < 4; i++) f.src[i] = f.dst[i] = f.sampler[i] = 0;
     f.src_len = f.dst_len = f.sampler_len = 0;
 }
