@@ -64,6 +64,7 @@ struct Flags {
     std::string Out = "-";                // -out: flows_5m rows (TSV); "-" = stdout
     std::string Key = "flows5m";          // -key: flows5m|aspair|srcaddr|dstaddr|5tuple|srcport|dstport
     int Devices = 1;                      // -gpus: partition p runs on GPU p mod gpus
+    std::string Format = "tsv";           // -format tsv | rowbinary: Clickhouse RowBinary of the flows_5m schema (create.sh:70-87)
     std::string Sink = "flows5m";         // -sink flows5m: roll-up rows (create.sh:70-87); rows: the inserter's own
                                           //       14-column row per flow (inserter.go:51-66,142-157)
     bool FlushBox = false;                // -flush.box: the closing flush is ONE exact roll-up over every partition (fa_flush_box)
@@ -127,6 +128,7 @@ static bool parse_flags(int argc, char **argv, Flags &f)
         else if (a == "out") f.Out = val();
         else if (a == "key") f.Key = val();
         else if (a == "sink") f.Sink = val();
+        else if (a == "format") f.Format = val();
         else if (a == "gpus") f.Devices = atoi(val().c_str());
         else if (a == "dry-run") f.DryRun = true;
         else if (a == "flush.box") f.FlushBox = true;
@@ -290,6 +292,7 @@ static std::string ip_string(const uint8_t *p, size_t len)
 // ---- state (inserter.go:75-88) --------------------------------------------------------------------
 static const char *kKeyNames[] = {"flows5m", "aspair", "srcaddr", "dstaddr", "5tuple", "srcport", "dstport"};
 static std::atomic<uint64_t> g_inserts{0};  // the insert_count counter (inserter.go:44-49)
+static std::atomic<uint64_t> g_rows{0}, g_bad{0}, g_flushes{0};  // roll-up rows written, undecodable messages, flushes
 static std::atomic<bool> g_stop{false};
 
 struct PartitionState {  // what one ConsumeClaim goroutine owns
@@ -299,6 +302,7 @@ struct PartitionState {  // what one ConsumeClaim goroutine owns
     uint32_t *offs = nullptr;
     size_t slab_cap = 0, rec_cap = 0, fill = 0, nrec = 0;
     std::vector<ConsumerMessage> pending;  // marked once their slab is submitted
+    uint64_t bad_seen = 0;                 // fa_stats.n_bad already added to the metrics
 };
 
 struct state {
@@ -402,6 +406,9 @@ struct state {
         fa_stats st;
         fa_stats_get(ps.ctx, &st);
         std::lock_guard<std::mutex> lk(out_mu);
+        g_bad += st.n_bad - ps.bad_seen;
+        ps.bad_seen = st.n_bad;
+        g_flushes++;
         bad = st.n_bad;
         for (size_t i = 0; i < n; i++) write_row(rows[i]);
         fflush(out);
@@ -444,8 +451,38 @@ struct state {
         fflush(out);
     }
 
+    // Clickhouse RowBinary of one flows_5m row: Date UInt16 (days), Timeslot DateTime UInt32, SrcAS, DstAS UInt32, the four
+    // one-element ETypeMap arrays (LEB128 length 1 + element), Bytes, Packets, Count UInt64 -- 70 bytes, little-endian;
+    // what `INSERT INTO flows_5m FORMAT RowBinary` takes (create.sh:70-87, :100-107)
+    void write_row_binary(const fa_row &r)
+    {
+        uint8_t b[70];
+        size_t o = 0;
+        auto put = [&](uint64_t v, int n) {
+            for (int i = 0; i < n; i++) b[o++] = (uint8_t)(v >> (8 * i));
+        };
+        put(r.key[0] / 86400u, 2);
+        put(r.key[0], 4);
+        put(r.key[1], 4);
+        put(r.key[2], 4);
+        put(1, 1);
+        put(r.key[3], 4);
+        put(1, 1);
+        put(r.bytes, 8);
+        put(1, 1);
+        put(r.packets, 8);
+        put(1, 1);
+        put(r.count, 8);
+        put(r.bytes, 8);
+        put(r.packets, 8);
+        put(r.count, 8);
+        fwrite(b, 1, o, out);
+    }
+
     void write_row(const fa_row &r)
     {
+        g_rows++;
+        if (key_mode == FA_KEY_FLOWS5M && fl.Format == "rowbinary") return write_row_binary(r);
         if (key_mode == FA_KEY_FLOWS5M) {
             // flows_5m columns (create.sh:70-87): Date, Timeslot, SrcAS, DstAS, ETypeMap.EType, .Bytes, .Packets,
             // .Count, Bytes, Packets, Count
@@ -503,11 +540,15 @@ struct state {
             exit(1);
         }
         bad = 0;
-        for (fa_ctx *c : ctxs) {
+        for (auto &ps : parts) {
+            if (!ps.ctx) continue;
             fa_stats st;
-            fa_stats_get(c, &st);
+            fa_stats_get(ps.ctx, &st);
             bad += st.n_bad;
+            g_bad += st.n_bad - ps.bad_seen;
+            ps.bad_seen = st.n_bad;
         }
+        g_flushes++;
         for (size_t i = 0; i < n; i++) write_row(rows[i]);
         fflush(out);
         rows_written += n;
@@ -537,9 +578,15 @@ static void metricsHTTP(const Flags &fl)
         char req[1024];
         ssize_t n = read(cfd, req, sizeof req - 1);
         (void)n;
-        char body[256], resp[512];
-        int bl = snprintf(body, sizeof body, "# HELP insert_count Inserts made to Postgres.\n# TYPE insert_count counter\ninsert_count %" PRIu64 "\n",
-                          g_inserts.load());
+        char body[1024], resp[1280];
+        int bl = snprintf(body, sizeof body,
+                          "# HELP insert_count Inserts made to Postgres.\n# TYPE insert_count counter\ninsert_count %" PRIu64 "\n"
+                          "# HELP flowagg_rollup_rows_total Aggregate rows written to the sink.\n# TYPE flowagg_rollup_rows_total counter\n"
+                          "flowagg_rollup_rows_total %" PRIu64 "\n"
+                          "# HELP flowagg_bad_records_total Messages proto.Unmarshal would reject (skipped, inserter.go:125).\n"
+                          "# TYPE flowagg_bad_records_total counter\nflowagg_bad_records_total %" PRIu64 "\n"
+                          "# HELP flowagg_flushes_total Roll-up flushes.\n# TYPE flowagg_flushes_total counter\nflowagg_flushes_total %" PRIu64 "\n",
+                          g_inserts.load(), g_rows.load(), g_bad.load(), g_flushes.load());
         int rl = snprintf(resp, sizeof resp, "HTTP/1.1 200 OK\r\nContent-Type: text/plain; version=0.0.4\r\nContent-Length: %d\r\n\r\n%s", bl, body);
         if (write(cfd, resp, (size_t)rl) < 0) {}
         close(cfd);

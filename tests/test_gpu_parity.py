@@ -396,6 +396,22 @@ def test_host_inserter_mirror_rows_equal_oracle(fp, oracle, torch_cuda, tmp_path
     want2 = [(time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(w["key"][0]))), str(w["key"][1]), str(w["key"][2]), f"[{w['key'][3]}]",
               str(w["bytes"]), str(w["packets"]), str(w["count"])) for w in merged]
     assert got2 == want2
+    # -format rowbinary: what `INSERT INTO flows_5m FORMAT RowBinary` takes (create.sh:70-87), 70 bytes per row
+    out3 = tmp_path / "rows_box.bin"
+    r = subprocess.run([exe, "-claim.file", ",".join(files), "-flush.count", "0", "-flush.dur", "1h", "-flush.box", "-format", "rowbinary",
+                        "-out", str(out3)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rb = np.dtype([("Date", "<u2"), ("Timeslot", "<u4"), ("SrcAS", "<u4"), ("DstAS", "<u4"), ("n0", "u1"), ("EType", "<u4"), ("n1", "u1"),
+                   ("MapBytes", "<u8"), ("n2", "u1"), ("MapPackets", "<u8"), ("n3", "u1"), ("MapCount", "<u8"), ("Bytes", "<u8"),
+                   ("Packets", "<u8"), ("Count", "<u8")])
+    assert rb.itemsize == 70
+    got3 = np.frombuffer(out3.read_bytes(), dtype=rb)
+    assert len(got3) == len(merged)
+    assert np.array_equal(got3["Timeslot"], merged["key"][:, 0]) and np.array_equal(got3["Date"], merged["key"][:, 0] // 86400)
+    assert np.array_equal(got3["SrcAS"], merged["key"][:, 1]) and np.array_equal(got3["DstAS"], merged["key"][:, 2])
+    assert np.array_equal(got3["EType"], merged["key"][:, 3]) and (got3["n0"] == 1).all() and (got3["n3"] == 1).all()
+    for a, b in (("Bytes", "bytes"), ("Packets", "packets"), ("Count", "count"), ("MapBytes", "bytes"), ("MapPackets", "packets"), ("MapCount", "count")):
+        assert np.array_equal(got3[a], merged[b]), a
 
 
 @pytest.mark.parametrize("mode,addr_mode,cms", [("flows5m", 0, False), ("aspair", 0, False), ("srcaddr", 1, True), ("dstport", 0, False)])
