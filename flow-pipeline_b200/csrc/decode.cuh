@@ -148,7 +148,12 @@ struct SmemSrc {
         uint32_t w0, w1, w2;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
         asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+#ifdef FA_W2_COND
+        // experiment: the third word is only needed for an unaligned cursor
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0;\n\t@p ld.shared.u32 %0, [%1+8];\n\t}" : "=r"(w2) : "r"(a), "r"(pos & 3u));
+#else
         asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
+#endif
         lo = funnel_r(w0, w1, sh);
         hi = funnel_r(w1, w2, sh);
     }

@@ -492,7 +492,10 @@ template <int MODE, bool WEIGHTED>
 struct AggConsumer {
     static constexpr int KW = KeyTraits<MODE>::KW;
     static constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
-    static constexpr int MIN_BLOCKS = KW <= 4 ? 8 : 5;  // 32 / 48 registers per thread
+#ifndef FA_AGG_MIN_BLOCKS
+#define FA_AGG_MIN_BLOCKS 8
+#endif
+    static constexpr int MIN_BLOCKS = KW <= 4 ? FA_AGG_MIN_BLOCKS : 5;  // 32 / 48 registers per thread
     static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     static constexpr bool PERMUTE = true;                // nothing is stored per record: lanes may take any record
     struct Item {

@@ -70,7 +70,8 @@ class FaMockerConfig(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libflowagg.so")
+    # FLOWAGG_LIB: another build of the same library (kernel experiments: profiles/r01/experiments)
+    return os.environ.get("FLOWAGG_LIB") or os.path.join(_HERE, "libflowagg.so")
 
 
 def build(verbose=False):
