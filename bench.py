@@ -398,7 +398,7 @@ def main():
             "config": {"workload": WORKLOAD, "flows_per_step_per_gpu": n_flows, "input_bytes_per_step_per_gpu": int(in_bytes),
                        "key": "(SrcAS,DstAS)", "groups": 65536, "slab_records": SLAB, "partitioning": "kafka partition = rank, one mocker instance (own seed, SequenceNum from 0) per partition",
                        "l2": "inputs (8.4 GB) larger than L2, streamed with L2 evict-first; the 16 MiB group table stays L2-resident by design", "table_slots": TABLE_CAP,
-                       "step": "fused decode+aggregate of every slab + flush (compact, D2H, ORDER BY on host)",
+                       "step": "fused decode+aggregate of every slab + flush (replica fold, compact, ORDER BY on the device, rows D2H)",
                        "box_merge": "per-rank roll-ups; the cross-rank row merge happens per 5-minute flush, outside the timed region"},
             "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
                          "traffic": ncu_traffic(), "kernel": "k_tile<AggConsumer<ASPAIR>> (fused decode+aggregate)",
