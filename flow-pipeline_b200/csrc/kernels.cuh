@@ -431,7 +431,6 @@ struct TileInfo {
     uint32_t b0;      // stream byte of the tile's first record
     uint32_t a0;      // b0 rounded down to 16: stream byte of shared-memory byte 0
     uint32_t s_end;   // stream byte one past the staged range (a0 if nothing is staged)
-    uint32_t span;    // bytes of the whole tile (0 if its offsets are not sane)
 };
 
 // Stage as much of the byte span of records [r0, r0+n) as fits into shared memory.
@@ -450,7 +449,6 @@ __device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t t
     uint32_t nbytes = 0;
     if (sane) nbytes = min((b1 - t.a0 + 15u) & ~15u, p.tile_bytes);
     t.s_end = t.a0 + nbytes;
-    t.span = sane ? b1 - t.b0 : 0u;
     const uint32_t bar = smem_u32(smem + p.tile_bytes + kTilePad);
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();

@@ -135,3 +135,31 @@ def test_host_inserter_mirror_flags_and_consume_loop(fp, tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "-claim.file", files[0]], capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_row_owner_is_a_balanced_deterministic_partition(fp, oracle):
+    """fa_row_owner (pure host function of the library): the hash partition of the box-wide exchange.  Same key ->
+    same owner whatever else the row holds, owners cover [0, n) evenly, invalid arguments are rejected."""
+    import importlib
+
+    par = importlib.import_module("flow-pipeline_b200.parallel")
+    cfg = fp.FaMockerConfig.make(seed=5, flows_per_second=100, addr_mode=1, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 40000)
+    for mode, kw in (("srcaddr", 4), ("5tuple", 11), ("aspair", 2), ("srcport", 1)):
+        rows, _, _ = oracle.run_batch(buf, offs, key_mode=mode)
+        rows = rows.view(fp.ROW_DTYPE)
+        for n in (2, 3, 8):
+            own = fp.row_owner(mode, rows, n)
+            assert own.max() < n
+            if len(rows) > 1000:
+                share = np.bincount(own, minlength=n) / len(rows)
+                assert share.min() > 0.6 / n and share.max() < 1.4 / n, (mode, n, share)
+            again = rows.copy()
+            again["bytes"] += 1                      # values do not matter, only the key words of the mode
+            again["key"][:, kw:] = 0xABCD
+            assert np.array_equal(fp.row_owner(mode, again, n), own)
+        grouped, counts = par.partition_rows(rows, mode, 4)
+        assert counts.sum() == len(rows) and np.array_equal(np.sort(fp.row_owner(mode, grouped, 4)), fp.row_owner(mode, grouped, 4))
+    L = fp.load_library()
+    assert L.fa_row_owner(99, None, 0, 2, None) != 0 and L.fa_row_owner(1, None, 0, 0, None) != 0
+    assert L.fa_row_owner(1, None, 0, 2, None) == 0
