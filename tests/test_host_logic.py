@@ -163,3 +163,38 @@ def test_row_owner_is_a_balanced_deterministic_partition(fp, oracle):
     L = fp.load_library()
     assert L.fa_row_owner(99, None, 0, 2, None) != 0 and L.fa_row_owner(1, None, 0, 0, None) != 0
     assert L.fa_row_owner(1, None, 0, 2, None) == 0
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` needs no GPU: one JSON line on stdout, the arm's keys, same metric/config naming as
+    the GPU arm; under torchrun every rank but 0 exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--flows", "300000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "flows/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("configs[1]") and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_gpu_arm_fails_loudly_without_a_gpu():
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-container check")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--flows", "100000"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
