@@ -767,3 +767,22 @@ def test_flush_box_is_the_exact_group_by_of_every_context(fp, oracle, torch_cuda
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_readme_sample_rows_on_the_gpu(fp, oracle, torch_cuda):
+    """The README's published flows_5m rows (README.md:180-183), same hand-made flows as the oracle's own pin test."""
+    from test_oracle_golden import _flow
+
+    t0 = 1584912398
+    msgs = [_flow(t0 + i % 2, 65001, d, b, p) for d, flows in ((65000, [(1000, 50), (1000, 50), (900, 50), (30, 2)]),
+                                                              (65001, [(1000, 90), (900, 90), (35, 10)]),
+                                                              (65002, [(1000, 48)] * 4 + [(400, 48), (420, 48)]))
+            for i, (b, p) in enumerate(flows)]
+    blob, offs = concat_records(msgs)
+    want, _, _ = oracle.run_batch(blob, offs, key_mode="flows5m", framed=False)
+    with fp.FlowAgg("flows5m") as a:
+        a.submit(blob, offs, framed=False)
+        rows = a.flush()
+    assert np.array_equal(rows, want)
+    assert [(int(r["key"][0]), int(r["key"][2]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in rows] == \
+        [(1584912300, 65000, 2930, 152, 4), (1584912300, 65001, 1935, 190, 3), (1584912300, 65002, 4820, 288, 6)]

@@ -126,3 +126,44 @@ def test_key_modes_and_cms(oracle, mocker_10k):
         r, _, _ = oracle.run_batch(g["blob"], g["offsets"], framed=False, key_mode=mode)
         assert len(r) == groups, mode
         assert r["bytes"].sum() == g["Bytes"].sum() and r["packets"].sum() == g["Packets"].sum()
+
+
+def _flow(t, src_as, dst_as, nbytes, pkts, etype=0x86DD):
+    """A mocker-shaped FlowMessage by hand: TimeReceived(2), SamplingRate(3), Bytes(9), Packets(10), SrcAS(14), DstAS(15), Etype(30)."""
+    def v(x):
+        out = bytearray()
+        while True:
+            b = x & 0x7F
+            x >>= 7
+            out.append(b | 0x80 if x else b)
+            if not x:
+                return bytes(out)
+    return (b"\x10" + v(t) + b"\x18\x01" + b"\x48" + v(nbytes) + b"\x50" + v(pkts) + b"\x70" + v(src_as) + b"\x78" + v(dst_as) +
+            b"\xf0\x01" + v(etype))
+
+
+def test_rollup_reproduces_the_readme_sample_rows(oracle):
+    """The only published output of the Clickhouse half (README.md:143-183): flows received at 2020-03-22 21:26:38/39 land in
+    Date 2020-03-22, Timeslot 21:25:00; `SELECT * FROM flows_5m WHERE SrcAS = 65001` shows one row per (SrcAS, DstAS) with
+    ETypeMap.EType [34525] and the nested sums equal to the row's own.  Flows chosen to add up to the README's three rows."""
+    import time
+
+    t0 = 1584912398  # 2020-03-22 21:26:38 UTC, README.md:155
+    assert time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(t0)) == "2020-03-22 21:26:38"
+    parts = {(65001, 65000): [(1000, 50), (1000, 50), (900, 50), (30, 2)],          # Bytes 2930, Packets 152, Count 4
+             (65001, 65001): [(1000, 90), (900, 90), (35, 10)],                      # 1935, 190, 3
+             (65001, 65002): [(1000, 48)] * 4 + [(400, 48), (420, 48)],              # 4820, 288, 6
+             (65000, 65002): [(7, 1)]}                                               # not selected by WHERE SrcAS = 65001
+    msgs = []
+    for (s, d), flows in parts.items():
+        for i, (b, p) in enumerate(flows):
+            msgs.append(_flow(t0 + (i % 2), s, d, b, p))
+    blob, offs = concat_records(msgs)
+    rows, _, res = oracle.run_batch(blob, offs, key_mode="flows5m", framed=False)
+    assert res["n_bad"] == 0
+    sel = rows[rows["key"][:, 1] == 65001]
+    got = [(time.strftime("%Y-%m-%d", time.gmtime(int(r["key"][0]))), time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(r["key"][0]))),
+            int(r["key"][1]), int(r["key"][2]), int(r["key"][3]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in sel]
+    assert got == [("2020-03-22", "2020-03-22 21:25:00", 65001, 65000, 34525, 2930, 152, 4),
+                   ("2020-03-22", "2020-03-22 21:25:00", 65001, 65001, 34525, 1935, 190, 3),
+                   ("2020-03-22", "2020-03-22 21:25:00", 65001, 65002, 34525, 4820, 288, 6)]   # README.md:180-183, in its ORDER BY order
