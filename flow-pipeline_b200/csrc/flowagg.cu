@@ -78,6 +78,15 @@ struct fa_ctx {
 
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
+    // the batch's field list for the decoder's lock-step fast path (decode.cuh): learned on the first submit and
+    // again whenever a flush/stats read shows the order-agnostic decoder took more than 1/8 of the records
+    uint16_t shape_tags[kShapeMax] = {0};
+    uint32_t shape_n = 0;
+    bool shape_known = false, shape_pinned = false, shape_relearn = false, shape_pending = false;
+    ShapeLearned *h_shape = nullptr;  // pinned landing area of k_learn_shape
+    cudaEvent_t ev_shape = nullptr;
+    uint64_t slow_seen = 0, records_seen = 0;  // counters at the last look
+
     uint64_t n_records = 0, n_submits = 0, bytes_in = 0;
     uint64_t last_groups = 0;  // rows of the previous flush: sizes the speculative (single-sync) flush
     uint64_t n_kernels = 0;  // launches of this library's own kernels (cub's are not counted)
@@ -116,7 +125,7 @@ extern "C" const char *fa_strerror(int s)
 
 extern "C" const char *fa_last_error(const fa_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 
-extern "C" const char *fa_build_info(void) { return "libflowagg abi=1 arch=sm_100a cuda=" FA_STR_CUDART; }
+extern "C" const char *fa_build_info(void) { return "libflowagg abi=" FA_STR(FA_ABI_VERSION) " arch=sm_100a cuda=" FA_STR_CUDART; }
 
 static int ensure_scratch(fa_ctx *c, size_t bytes)
 {
@@ -218,6 +227,8 @@ extern "C" void fa_destroy(fa_ctx *c)
     cudaFree(c->cols_block);
     cudaFree(c->d_scratch);
     cudaFreeHost(c->h_bounce);
+    cudaFreeHost(c->h_shape);
+    if (c->ev_shape) cudaEventDestroy(c->ev_shape);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -316,6 +327,8 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     // it had to be; not combining hot keys would be several times slower)
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
+    FA_CUDA(c, cudaHostAlloc(&c->h_shape, sizeof(ShapeLearned), cudaHostAllocDefault));
+    FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_shape, cudaEventDisableTiming));
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
         FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
         if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * kHotSlots * c->slot_bytes));
@@ -339,33 +352,26 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 // kernel launch
 // ---------------------------------------------------------------------------------------------
 
-template <class Consumer, int THREADS>
-static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
+template <class Consumer>
+static cudaError_t launch_tile(fa_ctx *c, TileParams &tp, uint32_t n_tiles)
 {
     const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;  // tile buffer + over-read pad + mbarrier
     static thread_local unsigned long long configured = 0;  // bit d: done for device d (per kernel instantiation, per thread)
     const unsigned long long dev_bit = 1ull << (c->cfg.device & 63);
     if (smem > 48 * 1024 && !(configured & dev_bit)) {  // the attribute is per device
-        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
+        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
         if (e != cudaSuccess) return e;
         configured |= dev_bit;
     }
-    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
+    // the batch's field list, narrowed to what this consumer keeps (decode.cuh: the lock-step fast path)
+    shape_build(c->shape_tags, c->shape_n, Consumer::NEED, tp.shape);
+    k_tile<Consumer><<<n_tiles, kTileRecords / Consumer::NR, smem, c->stream>>>(tp);
     c->n_kernels++;
     return cudaGetLastError();
 }
 
-template <class Consumer>
-static cudaError_t launch_tile(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
-{
-    if (tp.p.tile_records <= 128) return launch_tile_t<Consumer, 128>(c, tp, n_tiles);
-    if (tp.p.tile_records <= 256) return launch_tile_t<Consumer, 256>(c, tp, n_tiles);
-    if (tp.p.tile_records <= 512) return launch_tile_t<Consumer, 512>(c, tp, n_tiles);
-    return launch_tile_t<Consumer, 1024>(c, tp, n_tiles);
-}
-
 template <int MODE>
-static cudaError_t launch_fused_mode(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
+static cudaError_t launch_fused_mode(fa_ctx *c, TileParams &tp, uint32_t n_tiles)
 {
     return c->weighted ? launch_tile<AggConsumer<MODE, true>>(c, tp, n_tiles) : launch_tile<AggConsumer<MODE, false>>(c, tp, n_tiles);
 }
@@ -396,7 +402,7 @@ static cudaError_t launch_agg_columns_mode(fa_ctx *c, const SubmitParams &p, int
 static uint32_t pick_lane_stride(double avg)
 {
     static const int forced = getenv("FA_LANE_STRIDE") ? atoi(getenv("FA_LANE_STRIDE")) : 0;
-    if (forced > 0 && forced < 128 && ((forced & 1) || forced == 2 || forced == 4 || forced == 8)) return (uint32_t)forced;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return (uint32_t)forced;
     uint32_t best_d = 1, best_conf = 33;
     for (uint32_t d = 1; d <= 8; d *= 2) {
         uint32_t cnt[32] = {0}, conf = 0;
@@ -407,6 +413,40 @@ static uint32_t pick_lane_stride(double avg)
         }
     }
     return best_d;
+}
+
+// The batch's field list (decode.cuh: shape fast path).  First submit of a context: learn from this batch and wait
+// for the answer (once, ~20 us).  Later: re-learn asynchronously when asked to (shape_relearn, set where the
+// counters are read) and adopt the result when its event has fired.  p: buf/offsets/n_records/framed/base/len.
+static int shape_update(fa_ctx *c, const SubmitParams &p)
+{
+    if (c->shape_pinned) return FA_OK;
+    static const bool off = getenv("FA_SHAPE") && atoi(getenv("FA_SHAPE")) == 0;
+    if (off) {
+        c->shape_n = 0;
+        return FA_OK;
+    }
+    auto adopt = [&] {
+        c->shape_n = std::min<uint32_t>(c->h_shape->n, kShapeMax);
+        memcpy(c->shape_tags, c->h_shape->tagval, sizeof c->shape_tags);
+        c->shape_known = true;
+        c->shape_pending = false;
+    };
+    if (c->shape_pending && cudaEventQuery(c->ev_shape) == cudaSuccess) adopt();
+    cudaGetLastError();  // cudaErrorNotReady is not an error
+    if ((!c->shape_known || c->shape_relearn) && !c->shape_pending) {
+        k_learn_shape<<<1, 256, 0, c->stream>>>(p, c->h_shape);
+        c->n_kernels++;
+        FA_CUDA(c, cudaGetLastError());
+        FA_CUDA(c, cudaEventRecord(c->ev_shape, c->stream));
+        c->shape_pending = true;
+        c->shape_relearn = false;
+        if (!c->shape_known) {
+            FA_CUDA(c, cudaEventSynchronize(c->ev_shape));
+            adopt();
+        }
+    }
+    return FA_OK;
 }
 
 // Launch decode(+aggregate) over records already in device memory.
@@ -430,19 +470,22 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.hint_set = (uint32_t)(c->n_submits & 1u);
     if (c->d_hot) c->hot_dirty = true;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[p.hint_set][0], 0, 8, c->stream));  // this submit's statistics start at zero
-    // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
-    // the shared-memory budget, fewer for fat records
+    // tile shape from the batch's mean record size: 256 records per tile when their bytes fit
+    // the shared-memory budget (two buffers per CTA), fewer for fat records
     const double avg = (double)len / (double)n_records;
-    static const uint32_t max_tile = getenv("FA_TILE_RECORDS") ? (uint32_t)atoi(getenv("FA_TILE_RECORDS")) : (uint32_t)kThreads;
-    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~31u, 32u), 1024u);
-    while (tr > 32 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 32;
-    uint32_t tb = (uint32_t)((double)tr * avg * 1.06 + 512.0);
-    tb = (tb + 1023u) & ~1023u;
+    static const uint32_t max_tile = getenv("FA_TILE_RECORDS") ? (uint32_t)atoi(getenv("FA_TILE_RECORDS")) : (uint32_t)kTileRecords;
+    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~63u, 64u), (uint32_t)kTileRecords);
+    while (tr > 64 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 64;
+    uint32_t tb = (uint32_t)std::min<double>((double)tr * avg * 1.06 + 512.0, (double)kTileBytesMax);
+    tb = (tb + 511u) & ~511u;
     if (tb > (uint32_t)kTileBytesMax) tb = kTileBytesMax;
     if (tb < 4096u) tb = 4096u;
     p.tile_records = tr;
     p.tile_bytes = tb;
-    p.lane_stride = pick_lane_stride(avg);
+    const uint32_t d = tr == (uint32_t)kTileRecords ? pick_lane_stride(avg) : 1u;
+    p.lane_shift = d == 8 ? 3u : (d == 4 ? 2u : (d == 2 ? 1u : 0u));
+    int rc_shape = shape_update(c, p);
+    if (rc_shape) return rc_shape;
     tp.c = c->cols;
     const uint32_t n_tiles = (n_records + tr - 1) / tr;
     cudaError_t e = cudaSuccess;
@@ -603,6 +646,21 @@ extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32
     return FA_OK;
 }
 
+extern "C" int fa_set_shape(fa_ctx *c, const uint16_t *tag_values, uint32_t n)
+{
+    if (!c || n > kShapeMax || (n && !tag_values)) return FA_ERR_INVALID;
+    if (!tag_values) {  // back to learning from the data
+        c->shape_pinned = false;
+        c->shape_known = false;
+        c->shape_n = 0;
+        return FA_OK;
+    }
+    for (uint32_t i = 0; i < n; i++) c->shape_tags[i] = tag_values[i];
+    c->shape_n = n;
+    c->shape_pinned = true;
+    return FA_OK;
+}
+
 extern "C" int fa_sync(fa_ctx *c)
 {
     if (!c) return FA_ERR_INVALID;
@@ -612,10 +670,20 @@ extern "C" int fa_sync(fa_ctx *c)
     return FA_OK;
 }
 
+// the host just read the counters: did the shape fast path miss too often since the last look?
+static void shape_feedback(fa_ctx *c)
+{
+    const uint64_t slow = c->h_counters->n_slow, recs = c->n_records;
+    if (slow >= c->slow_seen && recs > c->records_seen && (slow - c->slow_seen) * 8 > recs - c->records_seen) c->shape_relearn = true;
+    c->slow_seen = slow;
+    c->records_seen = recs;
+}
+
 static int read_counters(fa_ctx *c)
 {
     FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));
+    shape_feedback(c);
     return FA_OK;
 }
 
@@ -636,6 +704,7 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
     out->n_submits = c->n_submits;
     out->bytes_in = c->bytes_in;
     out->n_kernels = c->n_kernels;
+    out->n_slow = c->h_counters->n_slow;
     return FA_OK;
 }
 
@@ -810,6 +879,7 @@ static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uin
     FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaMemcpyAsync(dst, rows_out, bytes, cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));  // the one wait
+    shape_feedback(c);
     const uint64_t groups = c->h_counters->n_groups, dropped = c->h_counters->n_dropped;
     if (groups > m) {  // the roll-up grew by more than 1/8: every row is still in scratch, the exact path takes over
         c->last_groups = groups;
@@ -1101,6 +1171,7 @@ extern "C" int fa_reset(fa_ctx *c)
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     c->n_records = c->n_submits = c->bytes_in = 0;
     c->n_kernels = 0;
+    c->slow_seen = c->records_seen = 0;
     return fa_sync(c);
 }
 

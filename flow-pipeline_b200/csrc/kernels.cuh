@@ -1,19 +1,20 @@
 // kernels.cuh -- sm_100a kernels of the flow-aggregation stage.
 //
-//   k_tile<AggConsumer<MODE,W>>  fused kernel 1 -> kernel 2: length-delimited
-//                                FlowMessage bytes -> group table (+ sketch).  The
-//                                columnar intermediate never touches HBM.
-//   k_tile<ColConsumer>          kernel 1 alone: bytes -> 20 decoded columns in HBM
-//                                (inserter.go:142-157 row + create.sh:36-59 columns).
-//   k_aggregate_columns<MODE>    kernel 2 alone: columns -> group table (+ sketch).
+//   k_tile<AggConsumer<MODE,W>>    fused kernel 1 -> kernel 2: length-delimited
+//                                  FlowMessage bytes -> group table (+ sketch).  The
+//                                  columnar intermediate never touches HBM.
+//   k_tile<ColConsumer>            kernel 1 alone: bytes -> 20 decoded columns in HBM
+//                                  (inserter.go:142-157 row + create.sh:36-59 columns).
+//   k_learn_shape                  the batch's field list for the decoder's lock-step fast path (decode.cuh).
+//   k_aggregate_columns<MODE>      kernel 2 alone: columns -> group table (+ sketch).
 //   k_table_init / k_merge_hot / k_compact_rows / k_estimate   table reset, hot-replica fold, flush, top-K candidates.
 //
-// Tile kernel: one CTA = one tile of <= 256 records.  The tile's byte span is
-// brought into shared memory by ONE bulk-async copy (cp.async.bulk, the 1-D TMA
-// path: SASS UBLKCP) signalled on an mbarrier, with an L2 evict-first policy so the
-// stream does not push the group table out of L2; then one thread parses one
-// record from shared memory.  Up to 8 CTAs are resident per SM, so copies of some
-// tiles overlap the parsing of others without any intra-CTA pipeline.
+// Tile kernel: one CTA = one tile of <= 256 records.  The tile's byte span is brought into shared memory by
+// ONE bulk-async copy (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) signalled on an mbarrier, with an L2
+// evict-first policy so the stream does not push the group table out of L2.  Each of the CTA's 128 threads then
+// parses TWO records side by side out of shared memory (decode.cuh: the lock-step field-list walk is paid once
+// for both, their loads overlap), and both records' group-table probes are in flight together.  Up to 8 CTAs are
+// resident per SM, so the copies of some tiles overlap the parsing of others without an intra-CTA pipeline.
 //
 // The path is integer / memory bound: no tensor cores anywhere.
 #pragma once
@@ -25,9 +26,13 @@
 
 namespace fa {
 
-constexpr int kThreads = 256;            // one record per thread per tile
+constexpr int kTileRecords = 256;        // records per tile (upper bound; fewer for fat records)
+constexpr int kThreads = 256;            // threads of the non-tile kernels
+// Tile CTAs: kTileRecords / NR threads, each parsing NR records side by side (Consumer::NR: 2 where the per-record state
+// is small -- the roll-ups with keys of <= 4 words -- 1 otherwise).  Either way 1024 threads' worth of records per SM
+// pair with 64 registers per thread: 8 CTAs of 128 threads or 4 of 256.
 constexpr int kTilePad = 64;             // over-read slack behind the tile (then the mbarrier)
-constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 24 KB)
+constexpr int kTileBytesMax = 200 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 23 KB)
 
 constexpr uint32_t kHotReplicas = 64;  // CTA b uses replica b mod 64
 constexpr uint32_t kHotSlots = 1024;   // slots per replica (power of two)
@@ -35,6 +40,7 @@ constexpr uint32_t kHotProbes = 8;     // bounded probe sequence; a miss falls t
 
 struct Counters {
     unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows;
+    unsigned long long n_slow;  // records the shape fast path did not decide (parsed by the order-agnostic decoder)
     unsigned int side_state, pad0;
     // key-repetition statistics of the two most recent submits: {lanes whose key repeats inside their warp,
     // lanes looked at}, sampled from every 64th tile.  Submit i decides from what submit i-1 saw.
@@ -48,9 +54,9 @@ struct SubmitParams {
     const uint32_t *offsets;  // n_records + 1
     uint32_t n_records;
     uint32_t framed;
-    uint32_t lane_stride;   // records between neighbouring lanes of a warp (host-chosen, see pick_lane_stride)
-    uint32_t tile_records;    // records per CTA tile (<= blockDim.x)
-    uint32_t tile_bytes;      // shared-memory bytes for the tile (multiple of 16); barrier sits behind it
+    uint32_t lane_shift;    // log2 of the records between neighbouring lanes of a warp (host-chosen, see pick_lane_stride)
+    uint32_t tile_records;    // records per tile (multiple of 64, <= kTileRecords)
+    uint32_t tile_bytes;      // shared-memory bytes for the tile (multiple of 16); the barrier sits behind it
     // group table
     uint8_t *slots;
     uint32_t slot_mask;
@@ -359,11 +365,33 @@ __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long lon
     }
 }
 
-// One decoded flow into the group table (+ sketch).  hot: this submit sends updates through the CTA's
-// replica first (keys repeat a lot: one shared slot per key would serialise in L2).
+// ---- one decoded flow into the group table (+ sketch), in two halves -----------------------------------
+//
+// begin: key, hash, sketch update, and the LOAD of the first slot of the probe sequence (hot replica or main table);
+// finish: compare, then the three reductions -- or, when the first slot is empty or holds another key, the ordinary
+// probe loop from the start (CAS claim included).  The stream kernel runs `finish` one tile after `begin`, so the
+// L2 round trip of the probe hides behind the parsing of the next record.
+template <int KW>
+struct Probe {
+    static constexpr int KEY64 = KW <= 2 ? 1 : 2;
+    uint8_t *table;                  // table (or hot replica) the probe runs in; nullptr = nothing in flight
+    uint32_t slot, mask;             // first slot of the probe sequence, slot mask of that table
+    unsigned long long k[KEY64];     // the flow's key
+    unsigned long long c[2][KEY64];  // what the first two slots of the sequence held
+    unsigned long long h, b, pk;
+    bool hot;
+};
+
+template <int KW>
+__device__ __forceinline__ uint8_t *hot_replica(const SubmitParams &p)
+{
+    return p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES;
+}
+
 // Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
 template <int MODE>
-__device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have)
+__device__ __forceinline__ uint32_t aggregate_begin(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have,
+                                                    Probe<(KeyTraits<MODE>::KW <= 4 ? KeyTraits<MODE>::KW : 1)> &pr)
 {
     constexpr int KW = KeyTraits<MODE>::KW;
     uint32_t key[KW];
@@ -378,14 +406,72 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         b *= f.sampling_rate;
         pk *= f.sampling_rate;
     }
-    if (p.slots) {
-        bool done = false;
-        if (KW <= 4 && hot)
-            done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, h, b, pk);
-        if (!done) table_add<KW>(p, key, h, b, pk, 1ull);
-    }
     if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
+    if (p.slots) {
+        if (KW > 4) {
+            table_add<KW>(p, key, h, b, pk, 1ull);  // wide keys: probed in place (state-word protocol)
+        } else {
+            constexpr int K4 = KW <= 4 ? KW : 1;
+            constexpr int HI = Probe<K4>::KEY64 - 1;
+            pr.k[0] = (unsigned long long)key[0] | (K4 >= 2 ? (unsigned long long)key[K4 >= 2 ? 1 : 0] << 32 : 0ull);
+            if (K4 == 4) pr.k[HI] = (unsigned long long)key[K4 == 4 ? 2 : 0] | ((unsigned long long)key[K4 == 4 ? 3 : 0] << 32);
+            const bool all_ones = K4 == 4 ? (pr.k[0] & pr.k[HI]) == ~0ull : pr.k[0] == ~0ull;
+            if (all_ones) {
+                side_slot_add<K4>(p, b, pk, 1ull);
+            } else {
+                pr.table = hot ? hot_replica<K4>(p) : p.slots;
+                pr.mask = hot ? kHotSlots - 1u : p.slot_mask;
+                pr.slot = (hot ? (uint32_t)(h >> 20) : (uint32_t)(h >> 32)) & pr.mask;
+                const uint8_t *s0 = pr.table + (size_t)pr.slot * SlotLayout<K4>::BYTES;
+                const uint8_t *s1 = pr.table + (size_t)((pr.slot + 1u) & pr.mask) * SlotLayout<K4>::BYTES;
+                if (K4 == 4) {
+                    ld_relaxed_u128(s0, pr.c[0][0], pr.c[0][HI]);
+                    ld_relaxed_u128(s1, pr.c[1][0], pr.c[1][HI]);
+                } else {
+                    pr.c[0][0] = ld_relaxed_u64(s0);
+                    pr.c[1][0] = ld_relaxed_u64(s1);
+                }
+                pr.h = h;
+                pr.b = b;
+                pr.pk = pk;
+                pr.hot = hot;
+            }
+        }
+    }
     return (uint32_t)h;
+}
+
+// The key sits in the first slot of its probe sequence that no other key holds: slot 0 if it matches; slot 1 if slot
+// 0 holds another key and slot 1 matches.  Everything else (an empty slot to claim, a longer sequence) is the
+// ordinary probe loop from the start.
+template <int KW>
+__device__ __forceinline__ void aggregate_finish(const SubmitParams &p, Probe<KW> &pr)
+{
+    if (!pr.table) return;
+    constexpr int HI = Probe<KW>::KEY64 - 1;
+    bool same0 = pr.c[0][0] == pr.k[0], same1 = pr.c[1][0] == pr.k[0];
+    bool empty0 = pr.c[0][0] == ~0ull;
+    if (KW == 4) {
+        same0 = same0 && pr.c[0][HI] == pr.k[HI];
+        same1 = same1 && pr.c[1][HI] == pr.k[HI];
+        empty0 = (pr.c[0][0] & pr.c[0][HI]) == ~0ull;
+    }
+    if (same0 || (same1 && !empty0)) {
+        const uint32_t slot = same0 ? pr.slot : ((pr.slot + 1u) & pr.mask);
+        slot_add(pr.table + (size_t)slot * SlotLayout<KW>::BYTES + SlotLayout<KW>::VAL_OFF, pr.b, pr.pk, 1ull);
+    } else {
+        uint32_t key[KW];
+        key[0] = (uint32_t)pr.k[0];
+        if (KW >= 2) key[KW >= 2 ? 1 : 0] = (uint32_t)(pr.k[0] >> 32);
+        if (KW == 4) {
+            key[KW == 4 ? 2 : 0] = (uint32_t)pr.k[HI];
+            key[KW == 4 ? 3 : 0] = (uint32_t)(pr.k[HI] >> 32);
+        }
+        bool done = false;
+        if (pr.hot) done = hot_add<KW>(pr.table, key, pr.h, pr.b, pr.pk);
+        if (!done) table_add<KW>(p, key, pr.h, pr.b, pr.pk, 1ull);
+    }
+    pr.table = nullptr;
 }
 
 // ---- tile staging: one bulk-async copy per tile ----------------------------------------------
@@ -395,7 +481,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -435,7 +520,7 @@ struct TileInfo {
 
 // Stage as much of the byte span of records [r0, r0+n) as fits into shared memory.
 // Records that end beyond s_end (oversized tiles, out-of-order offsets) are parsed
-// from global memory instead.
+// from global memory instead.  Stream positions fit 32 bits (offsets are u32).
 __device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t tile, uint8_t *smem)
 {
     TileInfo t;
@@ -444,18 +529,20 @@ __device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t t
     t.b0 = __ldg(p.offsets + t.r0);
     const uint32_t b1 = __ldg(p.offsets + t.r0 + t.n);
     t.a0 = t.b0 & ~15u;
-    const unsigned long long end = p.base + p.len;
-    const bool sane = t.b0 <= b1 && t.b0 >= p.base && (unsigned long long)b1 <= end;
-    uint32_t nbytes = 0;
-    if (sane) nbytes = min((b1 - t.a0 + 15u) & ~15u, p.tile_bytes);
+    const uint32_t base = (uint32_t)p.base, end = base + (uint32_t)p.len;
+    const bool sane = t.b0 <= b1 && t.b0 >= base && b1 <= end;
+    const uint32_t nbytes = sane ? min((b1 - t.a0 + 15u) & ~15u, p.tile_bytes) : 0u;
     t.s_end = t.a0 + nbytes;
     const uint32_t bar = smem_u32(smem + p.tile_bytes + kTilePad);
-    if (threadIdx.x == 0) mbar_init(bar, 1);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (nbytes) {
             mbar_expect_tx(bar, nbytes);
-            bulk_load(smem_u32(smem), p.buf + ((unsigned long long)t.a0 - p.base), nbytes, bar);
+            bulk_load(smem_u32(smem), p.buf + (t.a0 - base), nbytes, bar);
         } else {
             mbar_arrive(bar);
         }
@@ -475,7 +562,8 @@ struct Columns {
 
 struct TileParams {
     SubmitParams p;
-    Columns c;  // only read by ColConsumer
+    Columns c;         // only read by ColConsumer
+    ShapeTable shape;  // the batch's field list, specialised to the consumer's NEED mask (decode.cuh)
 };
 
 // ---- hot keys --------------------------------------------------------------------------------------
@@ -489,17 +577,24 @@ struct TileParams {
 template <int MODE, bool WEIGHTED>
 struct AggConsumer {
     static constexpr int KW = KeyTraits<MODE>::KW;
+    static constexpr int PKW = KW <= 4 ? KW : 1;  // layout of the in-flight probe (unused for wide keys)
     static constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
+#ifndef FA_AGG_NR
+#define FA_AGG_NR 1
+#endif
+    static constexpr int NR = KW <= 4 ? FA_AGG_NR : 1;   // records parsed side by side by one thread
 #ifndef FA_AGG_MIN_BLOCKS
 #define FA_AGG_MIN_BLOCKS 8
 #endif
-    static constexpr int MIN_BLOCKS = KW <= 4 ? FA_AGG_MIN_BLOCKS : 5;  // 32 / 48 registers per thread
+    static constexpr int MIN_BLOCKS = KW <= 4 ? FA_AGG_MIN_BLOCKS : 4;   // CTAs of 256 threads' worth of records per SM (32 / 64 registers)
     static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     static constexpr bool PERMUTE = true;                // nothing is stored per record: lanes may take any record
     struct Item {
         uint32_t h32;
         bool have;
     };
+    typedef Probe<PKW> State;
+    static __device__ __forceinline__ void state_clear(State &st) { st.table = nullptr; }
     static __device__ __forceinline__ void item_clear(Item &it)
     {
         it.h32 = 0;
@@ -511,20 +606,22 @@ struct AggConsumer {
         const unsigned int d = __ldg(&p.counters->hint[p.hint_set ^ 1u][0]), n = __ldg(&p.counters->hint[p.hint_set ^ 1u][1]);
         return n != 0u && d * 16u >= n;  // >= 1/16 of the sampled lanes repeat
     }
-    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
-                                                   Item &it)
+    // first half: everything up to the load of the first probe
+    static __device__ __forceinline__ void begin(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
+                                                 Item &it, State &st)
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have);
+            it.h32 = aggregate_begin<MODE>(tp.p, f, nokey, hot, it.have, st);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
     }
+    static __device__ __forceinline__ void finish(const TileParams &tp, State &st) { aggregate_finish<PKW>(tp.p, st); }
     // every 64th tile measures how often keys repeat inside a warp (feeds the next submit's decision)
-    static __device__ __forceinline__ void sample_repeats(const SubmitParams &p, const Item &it)
+    static __device__ __forceinline__ void sample_repeats(const SubmitParams &p, uint32_t tile, const Item &it)
     {
-        if (!HOT || (blockIdx.x & 63u) != 0u) return;
+        if (!HOT || (tile & 63u) != 0u) return;
         const uint32_t h32 = it.have ? it.h32 : (0x9E3779B9u * (threadIdx.x + 1u));
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h32);
         const uint32_t dups = __popc(__ballot_sync(0xFFFFFFFFu, it.have && __popc(peers) > 1));
@@ -545,17 +642,17 @@ __device__ __forceinline__ uint4 addr_bytes(const uint32_t be[4])
 
 struct ColConsumer {
     static constexpr uint32_t NEED = F_ALL;
-    static constexpr int MIN_BLOCKS = 4;  // all 16 fields live: 64 registers per thread
+    static constexpr int NR = 1;            // all 16 fields live: one record per thread
+    static constexpr int MIN_BLOCKS = 4;    // 64 registers
     static constexpr bool PERMUTE = false;  // column stores stay coalesced: lane i writes row r0+i
     struct Item {};
+    struct State {};
+    static __device__ __forceinline__ void state_clear(State &) {}
     static __device__ __forceinline__ void item_clear(Item &) {}
     static __device__ __forceinline__ bool want_hot(const SubmitParams &) { return false; }
-    static __device__ __forceinline__ void sample_repeats(const SubmitParams &, const Item &) {}
-    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool, Item &)
-    {
-        consume(tp, r, ok, f, bad, nokey);
-    }
-    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &)
+    static __device__ __forceinline__ void sample_repeats(const SubmitParams &, uint32_t, const Item &) {}
+    static __device__ __forceinline__ void finish(const TileParams &, State &) {}
+    static __device__ __forceinline__ void begin(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &, bool, Item &, State &)
     {
         const Columns &c = tp.c;
         if (!ok) {
@@ -585,10 +682,28 @@ struct ColConsumer {
     }
 };
 
+// A record the shape fast path did not decide, parsed by the order-agnostic decoder from the staged tile and consumed
+// on the spot.  Out of line with its own Flow, so the fast path keeps its Flow in registers.  Returns bad | nokey << 1.
+template <class Consumer>
+__device__ __noinline__ uint32_t record_from_tile(const TileParams &tp, uint32_t r, uint32_t smem_base, uint32_t p0, uint32_t p1, bool hot)
+{
+    uint32_t bad = 0, nokey = 0;
+    Flow f;
+    flow_reset(f);
+    SmemSrc s;
+    s.base = smem_base;
+    const bool ok = decode_record<Consumer::NEED>(s, p0, p1, tp.p.framed != 0, f);
+    typename Consumer::Item it;
+    typename Consumer::State st;
+    Consumer::item_clear(it);
+    Consumer::state_clear(st);
+    Consumer::begin(tp, r, ok, f, bad, nokey, hot, it, st);
+    Consumer::finish(tp, st);
+    return bad | (nokey << 1);
+}
+
 // one record straight from global memory (it did not fit the staged tile, or its
-// offsets are out of order): correct, slow, rare.  Out of line with its own Flow so
-// the hot path keeps its Flow in registers.
-// Returns bad | nokey << 1.
+// offsets are out of order): correct, slow, rare.  Returns bad | nokey << 1.
 template <class Consumer>
 __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32_t r, uint32_t o0, uint32_t o1)
 {
@@ -609,77 +724,167 @@ __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32
         ok = decode_record<Consumer::NEED>(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, f);
     }
     typename Consumer::Item it;
+    typename Consumer::State st;
     Consumer::item_clear(it);
-    Consumer::consume(tp, r, ok, f, bad, nokey, false, it);
+    Consumer::state_clear(st);
+    Consumer::begin(tp, r, ok, f, bad, nokey, false, it, st);
+    Consumer::finish(tp, st);
     return bad | (nokey << 1);
 }
 
-__device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad, uint32_t nokey)
+__device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad, uint32_t nokey, uint32_t slow)
 {
     bad = __reduce_add_sync(0xFFFFFFFFu, bad);
     nokey = __reduce_add_sync(0xFFFFFFFFu, nokey);
+    slow = __reduce_add_sync(0xFFFFFFFFu, slow);
     if ((threadIdx.x & 31) == 0) {
         if (bad) atomicAdd(&p.counters->n_bad, (unsigned long long)bad);
         if (nokey) atomicAdd(&p.counters->n_nokey, (unsigned long long)nokey);
+        if (slow) atomicAdd(&p.counters->n_slow, (unsigned long long)slow);
     }
 }
 
-// Which record of the tile does this thread parse?  Lanes of a warp read their records from shared memory in
-// lock step, so the bank pattern is set by the byte distance between the records of neighbouring lanes.  With
-// consecutive records and near-constant record sizes that distance can resonate with the 32 x 4-byte banks
-// (measured: 86-byte records = 21.5 words, 3 lanes apart = 64.5 words -> 3-4-way conflicts on every load, fused
-// kernel 0.87 ms instead of 0.56 ms).  Each warp therefore takes every d-th record of a run of 32*d records, with
-// d in {1,2,4,8} chosen per tile from its mean record size so that the predicted bank multiplicity is smallest.
-// Lane -> record mapping with d records between neighbouring lanes; a bijection on [0, THREADS) (THREADS = 2^k):
-// odd d: multiplication by a unit mod THREADS; d = 2^j: warps grouped in sets of d sharing 32*d consecutive records.
-template <int THREADS>
-__device__ __forceinline__ uint32_t record_of_thread(uint32_t d)
+// Which records of the tile does a thread parse?  Slot v of the tile's 256 parse slots is slot v / (256 / NR) of thread
+// v % (256 / NR).  Lanes of a warp read their records from shared memory in lock step, so the bank pattern is set by the
+// byte distance between the records of neighbouring lanes.  With consecutive records and near-constant record sizes
+// that distance can resonate with the 32 x 4-byte banks (measured: 86-byte records = 21.5 words, 3 lanes apart =
+// 64.5 words -> every third lane on one bank).  Each group of d = 2^shift 32-slot rows therefore shares a run of
+// 32*d records, neighbouring lanes taking records d apart; d is chosen per batch from its mean record size
+// (pick_lane_stride, host side).  A bijection on [0, kTileRecords).
+__device__ __forceinline__ uint32_t record_of_slot(uint32_t v, uint32_t shift)
 {
-    if (d & 1u) return (threadIdx.x * d) & (uint32_t)(THREADS - 1);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    return (warp / d) * 32u * d + lane * d + (warp % d);
+    const uint32_t lane = v & 31u, row = v >> 5;
+    return ((row >> shift) << (5u + shift)) + (lane << shift) + (row & ((1u << shift) - 1u));
 }
 
-// ---- the tile kernel: decode (+ consume) one tile per CTA ------------------------------------
+// ---- the tile kernel: decode (+ consume) one tile per CTA, kRecordsPerThread records per thread ----------------
 
-template <class Consumer, int THREADS>
-__global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / THREADS) k_tile(const __grid_constant__ TileParams tp)
+template <class Consumer>
+__global__ void __launch_bounds__(kTileRecords / Consumer::NR, Consumer::MIN_BLOCKS * Consumer::NR) k_tile(const __grid_constant__ TileParams tp)
 {
+    constexpr int NR = Consumer::NR, THREADS = kTileRecords / NR;
     extern __shared__ __align__(128) uint8_t smem[];
     const SubmitParams &p = tp.p;
     const TileInfo t = stage_tile(p, blockIdx.x, smem);
     const bool hot = Consumer::want_hot(p);  // uniform over the grid; the load overlaps the tile copy
-    uint32_t bad = 0, nokey = 0;
-    uint32_t in_tile = threadIdx.x;
-    // full tiles only (the mapping is a bijection on [0, THREADS)); short tails keep the identity
-    if (Consumer::PERMUTE && p.lane_stride > 1u && t.n == (uint32_t)THREADS && ((p.lane_stride & 1u) || (THREADS / 32) % p.lane_stride == 0))
-        in_tile = record_of_thread<THREADS>(p.lane_stride);
-    const bool active = in_tile < t.n;
-    const uint32_t r = t.r0 + in_tile;
-    uint32_t o0 = 0, o1 = 0;
-    if (active) {  // in flight while the bulk copy lands
-        o0 = __ldg(p.offsets + r);
-        o1 = __ldg(p.offsets + r + 1);
+    uint32_t bad = 0, nokey = 0, slow = 0;
+    uint32_t r[NR], o0[NR], o1[NR];
+    bool active[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+        uint32_t in_tile = threadIdx.x + q * THREADS;
+        // full tiles only (the mapping is a bijection on [0, kTileRecords)); short tails keep the identity
+        if (Consumer::PERMUTE && p.lane_shift && t.n == (uint32_t)kTileRecords) in_tile = record_of_slot(in_tile, p.lane_shift);
+        active[q] = in_tile < t.n;
+        r[q] = t.r0 + in_tile;
+        o0[q] = o1[q] = 0;
+        if (active[q]) {  // in flight while the bulk copy lands
+            o0[q] = __ldg(p.offsets + r[q]);
+            o1[q] = __ldg(p.offsets + r[q] + 1);
+        }
     }
     mbar_wait(smem_u32(smem + p.tile_bytes + kTilePad), 0);
-    typename Consumer::Item item;
-    Consumer::item_clear(item);
-    if (active) {
-        if (o0 >= t.b0 && o0 <= o1 && o1 <= t.s_end) {
-            Flow f;
-            flow_reset(f);
-            SmemSrc s;
-            s.base = smem_u32(smem);
-            const bool ok = decode_record<Consumer::NEED>(s, o0 - t.a0, o1 - t.a0, p.framed != 0, f);
-            Consumer::consume(tp, r, ok, f, bad, nokey, hot, item);
-        } else {
-            const uint32_t res = record_from_global<Consumer>(tp, r, o0, o1);  // updates the table itself
+
+    // every thread walks the field list for its NR records together (slots without a staged record walk an empty span);
+    // cursors are absolute shared-window addresses (the buffer is 16-byte aligned, so alignment arithmetic is unchanged)
+    const uint32_t buf = smem_u32(smem);
+    bool from_tile[NR], fast[NR];
+    uint32_t pos[NR], end[NR], p0[NR];
+    Flow f[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+        from_tile[q] = active[q] && o0[q] >= t.b0 && o0[q] <= o1[q] && o1[q] <= t.s_end;
+        p0[q] = pos[q] = buf + (from_tile[q] ? o0[q] - t.a0 : 0u);
+        end[q] = buf + (from_tile[q] ? o1[q] - t.a0 : 0u);
+        flow_reset(f[q]);
+    }
+    SmemSrc s;
+    s.base = 0u;
+    decode_records_shape<Consumer::NEED, NR>(tp.shape, s, pos, end, p.framed != 0, f, fast);
+
+    typename Consumer::Item item[NR];
+    typename Consumer::State state[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+        Consumer::item_clear(item[q]);
+        Consumer::state_clear(state[q]);
+        if (fast[q]) Consumer::begin(tp, r[q], true, f[q], bad, nokey, hot, item[q], state[q]);  // both probes in flight together
+    }
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+        Consumer::finish(tp, state[q]);
+        if (!fast[q] && active[q]) {  // not decided by the fast path: the order-agnostic decoder, consumed on the spot
+            uint32_t res;
+            if (from_tile[q]) {
+                slow++;
+                res = record_from_tile<Consumer>(tp, r[q], 0u, p0[q], end[q], hot);
+            } else {
+                res = record_from_global<Consumer>(tp, r[q], o0[q], o1[q]);
+            }
             bad += res & 1u;
             nokey += res >> 1;
         }
+        Consumer::sample_repeats(p, blockIdx.x, item[q]);
     }
-    Consumer::sample_repeats(p, item);
-    flush_counts(p, bad, nokey);
+    flush_counts(p, bad, nokey, slow);
+}
+
+// ---- the batch's field list ------------------------------------------------------------------------------
+//
+// 256 records spread over the batch are walked (shape_collect, decode.cuh) and every tag a fast-path step could
+// stand for is marked; the ascending list of marked tag values goes to (pinned) host memory, where the next launches
+// turn it into their ShapeTable.  Purely a speed matter: results never depend on the table.
+struct ShapeLearned {
+    uint32_t n;      // tag values written (0 when more than kShapeMax distinct tags were seen: no fast path)
+    uint32_t total;  // distinct tags seen
+    uint16_t tagval[kShapeMax];
+};
+
+struct MarkTag {
+    unsigned int *bits;  // three bitmaps of 2^14 bits: tag seen | with a 1..4-byte varint | with a 5-byte varint
+    __device__ __forceinline__ void operator()(uint32_t tagval, uint32_t vb) const
+    {
+        const uint32_t w = (tagval >> 5) & 511u, bit = 1u << (tagval & 31u);
+        atomicOr(&bits[w], bit);
+        if (vb >= 1u && vb <= 4u) atomicOr(&bits[512u + w], bit);
+        if (vb == 5u) atomicOr(&bits[1024u + w], bit);
+    }
+};
+
+__global__ void __launch_bounds__(256) k_learn_shape(const SubmitParams p, ShapeLearned *out)
+{
+    __shared__ unsigned int bits[3 * 512];  // one bit per tag value < 2^14, three times (MarkTag)
+    for (uint32_t i = threadIdx.x; i < 3u * 512u; i += blockDim.x) bits[i] = 0u;
+    __syncthreads();
+    const uint32_t n = p.n_records;
+    const uint32_t r = n >= 256u ? (uint32_t)(((unsigned long long)threadIdx.x * n) >> 8) : threadIdx.x;
+    if (r < n) {
+        const uint32_t o0 = __ldg(p.offsets + r), o1 = __ldg(p.offsets + r + 1);
+        if (o0 < o1 && o0 >= p.base && (unsigned long long)o1 <= p.base + p.len) {
+            ByteSrc s;
+            s.words = reinterpret_cast<const uint32_t *>(p.buf);
+            s.limit_word = (uint32_t)(((p.len + 15ull) & ~15ull) / 4ull) - 1u;
+            shape_collect(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, MarkTag{bits});
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t m = 0;
+        for (uint32_t w = 0; w < 512u; w++) {
+            unsigned int v = bits[w];
+            while (v) {
+                const uint32_t bit = __ffs((int)v) - 1u;
+                v &= v - 1u;
+                if (m < kShapeMax)
+                    out->tagval[m] = (uint16_t)((w * 32u + bit) | (((bits[512u + w] >> bit) & 1u) ? kTagSaw4 : 0u) |
+                                                (((bits[1024u + w] >> bit) & 1u) ? kTagSaw5 : 0u));
+                m++;
+            }
+        }
+        out->total = m;
+        out->n = m <= kShapeMax ? m : 0u;
+        __threadfence_system();
+    }
 }
 
 // ---- kernel 2 alone: columns -> table / sketch -------------------------------------------------
@@ -716,9 +921,12 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
             f.dst_len = c.dst_addr_len[r] == 255 ? 17u : c.dst_addr_len[r];
         }
         bool have;
-        aggregate_flow<MODE>(p, f, nokey, false, have);
+        Probe<(KeyTraits<MODE>::KW <= 4 ? KeyTraits<MODE>::KW : 1)> pr;
+        pr.table = nullptr;
+        aggregate_begin<MODE>(p, f, nokey, false, have, pr);
+        aggregate_finish(p, pr);
     }
-    flush_counts(p, 0, nokey);
+    flush_counts(p, 0, nokey, 0);
 }
 
 // ---- table reset / flush / top-K candidates ----------------------------------------------------------
