@@ -40,10 +40,16 @@ WORKLOAD = "configs[1]: 100M mocker FlowMessages, (SrcAS,DstAS) group-by sum(Byt
 METRIC = "flows/sec aggregated (decode+aggregate); achieved HBM GB/s vs peak"
 
 
+def bench_config():
+    """The workload's name tag, identical for both arms (the driver compares the two lines' config)."""
+    return {"workload": WORKLOAD, "flows_per_step_per_gpu": N_FLOWS, "key": "(SrcAS,DstAS)", "groups": 65536,
+            "partitioning": "kafka partition = rank, one mocker instance (own seed, SequenceNum from 0) per partition"}
+
+
 def mocker_cfg(fp, partition=0):
     # 250k flows/s of stream time: 100M flows span 400 s = two five-minute slots.  One mocker instance per Kafka
     # partition: its own random stream (seed) and its own SequenceNum counter from 0 (`var i uint32`, mocker/mocker.go:52,89)
-    return fp.FaMockerConfig.make(seed=1 + partition, flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True)
+    return fp.FaMockerConfig.make(seed=1 + partition, **MOCKER)
 
 
 def measured_peak():
@@ -134,31 +140,39 @@ def cgroup_throttle():
 
 
 def cpu_oracle_run(slabs, threads):
-    """The CPU restatement (oracle/flow_oracle.c) over host slabs [(bytes, offsets)], all threads."""
+    """The CPU restatement (oracle/flow_oracle.c) over host slabs [(bytes, offsets)], all threads.  Built with
+    -march=native on this host the first time it is used here (oracle.use_native)."""
     from oracle import oracle as o
 
+    o.use_native()
     return o.run_slabs(slabs, framed=True, key_mode="aspair", threads=threads)
 
 
-def host_slabs(fp, cfg, first, n_flows, slab):
-    """mocker-distribution input generated on the host cores, one thread per slab chunk."""
+MOCKER = dict(flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True)  # mocker_cfg() below, as plain numbers
+
+
+def host_slabs(partition, first, n_flows, slab):
+    """mocker-distribution input generated on the host cores by oracle/libmocker_ref.so (the same (seed, index) ->
+    bytes function as the GPU arm's generator, without mapping the product library), one thread per slab chunk."""
     from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as o
 
     jobs = [(first + a, min(slab, n_flows - a)) for a in range(0, n_flows, slab)]
     with ThreadPoolExecutor(max_workers=min(len(jobs), usable_cores())) as ex:
-        return list(ex.map(lambda j: fp.mocker_host(cfg, j[0], j[1]), jobs))
+        return list(ex.map(lambda j: o.mocker_host(seed=1 + partition, first=j[0], n=j[1], **MOCKER), jobs))
 
 
 def run_reference(args, rank, world, emit):
     """--impl reference: the CPU restatement of the reference path on the host cores (rank 0 only)."""
     if rank != 0:
         return 0
-    import flow_pipeline_b200 as fp
+    from oracle import oracle as o
 
     cores = usable_cores()
     n = min(args.flows, max(1 << 22, min(N_FLOWS, (1 << 21) * cores)))  # bounded sample of the same stream
-    cfg = mocker_cfg(fp)
-    slabs = host_slabs(fp, cfg, 0, n, 1 << 20)
+    isa = o.use_native()
+    slabs = host_slabs(0, 0, n, 1 << 20)
     times = []
     for i in range(args.warmup + args.steps):
         rows, res = cpu_oracle_run(slabs, cores)
@@ -171,10 +185,12 @@ def run_reference(args, rank, world, emit):
         "metric": METRIC, "value": v, "unit": "flows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": WORKLOAD, "flows_per_step": n, "key": "(SrcAS,DstAS)", "groups": 65536,
+        "config": bench_config(),
+        "detail": {"flows_per_timed_step": n,
                    "note": "Go inserter + Clickhouse cannot run here (no Go toolchain/DB); this is the C restatement "
-                           "oracle/flow_oracle.c, all host threads, per-thread tables merged in parallel at the end"},
-        "cpu_baseline": {"value": v, "unit": "flows/s", "cores": cores, "kind": "port",
+                           f"oracle/flow_oracle.c ({isa} build), all host threads, per-thread tables merged in parallel at the end; "
+                           "input from oracle/libmocker_ref.so (the product library is not mapped by this arm)"},
+        "cpu_baseline": {"value": v, "unit": "flows/s", "cores": cores, "kind": "port", "isa": isa,
                          "sample": f"{n} flows of the same stream per step, {cores} pthreads (cgroup quota; os.cpu_count()={os.cpu_count()})"},
         "e2e": {"value": v, "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -395,8 +411,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "flows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "flows_per_step_per_gpu": n_flows, "input_bytes_per_step_per_gpu": int(in_bytes),
-                       "key": "(SrcAS,DstAS)", "groups": 65536, "slab_records": SLAB, "partitioning": "kafka partition = rank, one mocker instance (own seed, SequenceNum from 0) per partition",
+            "config": bench_config(),
+            "detail": {"flows_per_timed_step": n_flows, "input_bytes_per_step_per_gpu": int(in_bytes), "slab_records": SLAB,
                        "l2": "inputs (8.4 GB) larger than L2, streamed with L2 evict-first; the 16 MiB group table stays L2-resident by design", "table_slots": TABLE_CAP,
                        "step": "fused decode+aggregate of every slab + flush (replica fold, compact, ORDER BY on the device, rows D2H)",
                        "box_merge": "per-rank roll-ups; the cross-rank row merge happens per 5-minute flush, outside the timed region"},

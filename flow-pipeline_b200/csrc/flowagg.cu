@@ -87,6 +87,12 @@ struct fa_ctx {
     cudaEvent_t ev_shape = nullptr;
     uint64_t slow_seen = 0, records_seen = 0;  // counters at the last look
 
+    // device time of the decode/aggregate kernels: an event pair around every launch, read back lazily
+    static constexpr int kBusyRing = 32;
+    cudaEvent_t ev_busy[kBusyRing][2] = {};
+    uint64_t busy_head = 0, busy_tail = 0;  // pairs recorded / pairs added to busy_us
+    double busy_us = 0;
+
     uint64_t n_records = 0, n_submits = 0, bytes_in = 0;
     uint64_t last_groups = 0;  // rows of the previous flush: sizes the speculative (single-sync) flush
     uint64_t n_kernels = 0;  // launches of this library's own kernels (cub's are not counted)
@@ -229,6 +235,9 @@ extern "C" void fa_destroy(fa_ctx *c)
     cudaFreeHost(c->h_bounce);
     cudaFreeHost(c->h_shape);
     if (c->ev_shape) cudaEventDestroy(c->ev_shape);
+    for (auto &pair : c->ev_busy)
+        for (cudaEvent_t e : pair)
+            if (e) cudaEventDestroy(e);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -355,17 +364,21 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 template <class Consumer>
 static cudaError_t launch_tile(fa_ctx *c, TileParams &tp, uint32_t n_tiles)
 {
-    const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;  // tile buffer + over-read pad + mbarrier
+    const size_t smem = 2 * ((size_t)tp.p.tile_bytes + kTilePad + kStreamOffBytes) + kStreamCtlBytes;  // two tile buffers, two offsets slices, barriers/counters/bounds
     static thread_local unsigned long long configured = 0;  // bit d: done for device d (per kernel instantiation, per thread)
     const unsigned long long dev_bit = 1ull << (c->cfg.device & 63);
-    if (smem > 48 * 1024 && !(configured & dev_bit)) {  // the attribute is per device
-        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
+    if (!(configured & dev_bit)) {  // the attribute is per device
+        cudaError_t e = cudaFuncSetAttribute(k_stream<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(2 * (kTileBytesMax + kTilePad + kStreamOffBytes) + kStreamCtlBytes));
         if (e != cudaSuccess) return e;
         configured |= dev_bit;
     }
     // the batch's field list, narrowed to what this consumer keeps (decode.cuh: the lock-step fast path)
     shape_build(c->shape_tags, c->shape_n, Consumer::NEED, tp.shape);
-    k_tile<Consumer><<<n_tiles, kTileRecords / Consumer::NR, smem, c->stream>>>(tp);
+    tp.p.n_tiles = n_tiles;
+    tp.p.offsets_aligned = ((uintptr_t)tp.p.offsets & 15u) == 0 ? 1u : 0u;
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(c->num_sms * kStreamBlocksPerSM));  // persistent CTAs
+    k_stream<Consumer><<<grid, kThreads, smem, c->stream>>>(tp);
     c->n_kernels++;
     return cudaGetLastError();
 }
@@ -449,6 +462,20 @@ static int shape_update(fa_ctx *c, const SubmitParams &p)
     return FA_OK;
 }
 
+// Add the device time of launches whose event pairs have completed (all of them when wait is set).
+static void busy_collect(fa_ctx *c, bool wait)
+{
+    while (c->busy_tail < c->busy_head) {
+        cudaEvent_t *pair = c->ev_busy[c->busy_tail % fa_ctx::kBusyRing];
+        if (wait) cudaEventSynchronize(pair[1]);
+        else if (cudaEventQuery(pair[1]) != cudaSuccess) break;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pair[0], pair[1]) == cudaSuccess) c->busy_us += (double)ms * 1e3;
+        c->busy_tail++;
+    }
+    cudaGetLastError();  // cudaErrorNotReady is not an error
+}
+
 // Launch decode(+aggregate) over records already in device memory.
 static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t len, const uint32_t *d_offsets,
                         uint32_t n_records, uint32_t flags)
@@ -474,8 +501,8 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     // the shared-memory budget (two buffers per CTA), fewer for fat records
     const double avg = (double)len / (double)n_records;
     static const uint32_t max_tile = getenv("FA_TILE_RECORDS") ? (uint32_t)atoi(getenv("FA_TILE_RECORDS")) : (uint32_t)kTileRecords;
-    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~63u, 64u), (uint32_t)kTileRecords);
-    while (tr > 64 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 64;
+    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~31u, 32u), (uint32_t)kTileRecords);
+    while (tr > 32 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 32;
     uint32_t tb = (uint32_t)std::min<double>((double)tr * avg * 1.06 + 512.0, (double)kTileBytesMax);
     tb = (tb + 511u) & ~511u;
     if (tb > (uint32_t)kTileBytesMax) tb = kTileBytesMax;
@@ -489,6 +516,13 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     tp.c = c->cols;
     const uint32_t n_tiles = (n_records + tr - 1) / tr;
     cudaError_t e = cudaSuccess;
+    busy_collect(c, c->busy_head - c->busy_tail >= (uint64_t)fa_ctx::kBusyRing);  // a full ring waits for its oldest pair
+    cudaEvent_t *busy = c->ev_busy[c->busy_head % fa_ctx::kBusyRing];
+    if (!busy[0]) {
+        FA_CUDA(c, cudaEventCreate(&busy[0]));
+        FA_CUDA(c, cudaEventCreate(&busy[1]));
+    }
+    FA_CUDA(c, cudaEventRecord(busy[0], c->stream));
     if (c->cfg.flags & FA_CFG_COLUMNS) {
         if (n_records > c->cfg.max_batch_records) return FA_ERR_INVALID;
         e = launch_tile<ColConsumer>(c, tp, n_tiles);
@@ -505,6 +539,8 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
 #undef CALL_FUSED
     }
     FA_CUDA(c, e);
+    FA_CUDA(c, cudaEventRecord(busy[1], c->stream));
+    c->busy_head++;
     c->n_submits++;
     c->n_records += n_records;
     return FA_OK;
@@ -705,6 +741,8 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
     out->bytes_in = c->bytes_in;
     out->n_kernels = c->n_kernels;
     out->n_slow = c->h_counters->n_slow;
+    busy_collect(c, true);
+    out->gpu_busy_us = (uint64_t)c->busy_us;
     return FA_OK;
 }
 
@@ -1172,6 +1210,8 @@ extern "C" int fa_reset(fa_ctx *c)
     c->n_records = c->n_submits = c->bytes_in = 0;
     c->n_kernels = 0;
     c->slow_seen = c->records_seen = 0;
+    busy_collect(c, true);
+    c->busy_us = 0;
     return fa_sync(c);
 }
 
@@ -1348,19 +1388,23 @@ std::mutex g_nccl_mu;
 bool nccl_load(std::string &err)
 {
     if (g_nccl.lib) return true;
+    // resolve everything into a local copy and publish it only when complete: a half-loaded table must never be
+    // mistaken for a loaded one by the next call
+    NcclApi api;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {
-        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (g_nccl.lib) break;
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
     }
-    if (!g_nccl.lib) {
+    if (!api.lib) {
         err = std::string("dlopen libnccl.so.2 failed: ") + dlerror();
         return false;
     }
 #define SYM(f, name)                                              \
-    *(void **)(&g_nccl.f) = dlsym(g_nccl.lib, name);              \
-    if (!g_nccl.f) {                                              \
+    *(void **)(&api.f) = dlsym(api.lib, name);                    \
+    if (!api.f) {                                                 \
         err = std::string("missing NCCL symbol ") + name;         \
+        dlclose(api.lib);                                         \
         return false;                                             \
     }
     SYM(CommInitAll, "ncclCommInitAll")
@@ -1370,6 +1414,7 @@ bool nccl_load(std::string &err)
     SYM(AllReduce, "ncclAllReduce")
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+    g_nccl = api;
     return true;
 }
 }  // namespace
@@ -1392,11 +1437,15 @@ extern "C" int fa_topk(fa_ctx *const *ctxs, int n_ctx, size_t k, fa_hh *out, siz
         std::vector<int> devs(n_ctx);
         for (int i = 0; i < n_ctx; i++) devs[i] = ctxs[i]->cfg.device;
         if (g_nccl.devs != devs) {
-            for (ncclComm_t cm : g_nccl.comms) g_nccl.CommDestroy(cm);
+            for (ncclComm_t cm : g_nccl.comms)
+                if (cm) g_nccl.CommDestroy(cm);
+            g_nccl.devs.clear();
             g_nccl.comms.assign(n_ctx, nullptr);
             int r = g_nccl.CommInitAll(g_nccl.comms.data(), n_ctx, devs.data());
             if (r != 0) {
                 c0->last_error = std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r);
+                for (ncclComm_t cm : g_nccl.comms)  // a partial init may have produced some communicators
+                    if (cm) g_nccl.CommDestroy(cm);
                 g_nccl.comms.clear();
                 g_nccl.devs.clear();
                 return FA_ERR_NCCL;

@@ -1,20 +1,21 @@
 // kernels.cuh -- sm_100a kernels of the flow-aggregation stage.
 //
-//   k_tile<AggConsumer<MODE,W>>    fused kernel 1 -> kernel 2: length-delimited
+//   k_stream<AggConsumer<MODE,W>>  fused kernel 1 -> kernel 2: length-delimited
 //                                  FlowMessage bytes -> group table (+ sketch).  The
 //                                  columnar intermediate never touches HBM.
-//   k_tile<ColConsumer>            kernel 1 alone: bytes -> 20 decoded columns in HBM
+//   k_stream<ColConsumer>          kernel 1 alone: bytes -> 20 decoded columns in HBM
 //                                  (inserter.go:142-157 row + create.sh:36-59 columns).
 //   k_learn_shape                  the batch's field list for the decoder's lock-step fast path (decode.cuh).
 //   k_aggregate_columns<MODE>      kernel 2 alone: columns -> group table (+ sketch).
 //   k_table_init / k_merge_hot / k_compact_rows / k_estimate   table reset, hot-replica fold, flush, top-K candidates.
 //
-// Tile kernel: one CTA = one tile of <= 256 records.  The tile's byte span is brought into shared memory by
-// ONE bulk-async copy (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) signalled on an mbarrier, with an L2
-// evict-first policy so the stream does not push the group table out of L2.  Each of the CTA's 128 threads then
-// parses TWO records side by side out of shared memory (decode.cuh: the lock-step field-list walk is paid once
-// for both, their loads overlap), and both records' group-table probes are in flight together.  Up to 8 CTAs are
-// resident per SM, so the copies of some tiles overlap the parsing of others without an intra-CTA pipeline.
+// Stream kernel: persistent CTAs (4 per SM, 256 threads), each walking tiles of <= 256 records.  A tile's byte
+// span AND its slice of the offsets array are brought into one of the CTA's TWO shared-memory buffers by bulk-async
+// copies (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) signalled on an mbarrier, with an L2 evict-first policy so
+// the stream does not push the group table out of L2.  While the 8 warps parse tile k out of one buffer (one thread
+// = one record), the copy of tile k+1 lands in the other; the warp that finishes reading a buffer LAST re-arms it
+// with tile k+2 (its byte bounds were fetched by warp 0 a whole parse earlier and handed over through shared
+// memory), so no warp ever waits at a block-wide barrier and no global load sits between two tiles.
 //
 // The path is integer / memory bound: no tensor cores anywhere.
 #pragma once
@@ -26,13 +27,13 @@
 
 namespace fa {
 
-constexpr int kTileRecords = 256;        // records per tile (upper bound; fewer for fat records)
-constexpr int kThreads = 256;            // threads of the non-tile kernels
-// Tile CTAs: kTileRecords / NR threads, each parsing NR records side by side (Consumer::NR: 2 where the per-record state
-// is small -- the roll-ups with keys of <= 4 words -- 1 otherwise).  Either way 1024 threads' worth of records per SM
-// pair with 64 registers per thread: 8 CTAs of 128 threads or 4 of 256.
-constexpr int kTilePad = 64;             // over-read slack behind the tile (then the mbarrier)
-constexpr int kTileBytesMax = 200 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 23 KB)
+constexpr int kThreads = 256;            // one record per thread per tile
+constexpr int kTileRecords = kThreads;
+constexpr int kTilePad = 64;             // over-read slack behind each tile buffer
+constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile buffer, upper bound (mocker tile of 256: 21.6 KB -> 23 KB)
+constexpr int kStreamBlocksPerSM = 4;    // 2 x 23 KB buffers per CTA: 4 CTAs = 32 warps per SM, 64 registers per thread
+constexpr int kStreamOffBytes = (kThreads + 8) * 4;  // a tile's slice of the offsets array (n+1 words), per buffer
+constexpr int kStreamCtlBytes = 64;      // mbarriers, reader counters, tile bounds behind the buffers
 
 constexpr uint32_t kHotReplicas = 64;  // CTA b uses replica b mod 64
 constexpr uint32_t kHotSlots = 1024;   // slots per replica (power of two)
@@ -55,8 +56,10 @@ struct SubmitParams {
     uint32_t n_records;
     uint32_t framed;
     uint32_t lane_shift;    // log2 of the records between neighbouring lanes of a warp (host-chosen, see pick_lane_stride)
-    uint32_t tile_records;    // records per tile (multiple of 64, <= kTileRecords)
-    uint32_t tile_bytes;      // shared-memory bytes for the tile (multiple of 16); the barrier sits behind it
+    uint32_t tile_records;    // records per tile (multiple of 32, <= kTileRecords)
+    uint32_t tile_bytes;      // shared-memory bytes per tile buffer (multiple of 16)
+    uint32_t n_tiles;
+    uint32_t offsets_aligned;  // offsets is 16-byte aligned: a tile's slice of it can be staged by a bulk copy
     // group table
     uint8_t *slots;
     uint32_t slot_mask;
@@ -374,10 +377,9 @@ __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long lon
 template <int KW>
 struct Probe {
     static constexpr int KEY64 = KW <= 2 ? 1 : 2;
-    uint8_t *table;                  // table (or hot replica) the probe runs in; nullptr = nothing in flight
-    uint32_t slot, mask;             // first slot of the probe sequence, slot mask of that table
+    uint8_t *slot;                   // first slot of the probe sequence; nullptr = nothing in flight
     unsigned long long k[KEY64];     // the flow's key
-    unsigned long long c[2][KEY64];  // what the first two slots of the sequence held
+    unsigned long long c[KEY64];     // what the slot held
     unsigned long long h, b, pk;
     bool hot;
 };
@@ -419,18 +421,11 @@ __device__ __forceinline__ uint32_t aggregate_begin(const SubmitParams &p, const
             if (all_ones) {
                 side_slot_add<K4>(p, b, pk, 1ull);
             } else {
-                pr.table = hot ? hot_replica<K4>(p) : p.slots;
-                pr.mask = hot ? kHotSlots - 1u : p.slot_mask;
-                pr.slot = (hot ? (uint32_t)(h >> 20) : (uint32_t)(h >> 32)) & pr.mask;
-                const uint8_t *s0 = pr.table + (size_t)pr.slot * SlotLayout<K4>::BYTES;
-                const uint8_t *s1 = pr.table + (size_t)((pr.slot + 1u) & pr.mask) * SlotLayout<K4>::BYTES;
-                if (K4 == 4) {
-                    ld_relaxed_u128(s0, pr.c[0][0], pr.c[0][HI]);
-                    ld_relaxed_u128(s1, pr.c[1][0], pr.c[1][HI]);
-                } else {
-                    pr.c[0][0] = ld_relaxed_u64(s0);
-                    pr.c[1][0] = ld_relaxed_u64(s1);
-                }
+                uint8_t *s = hot ? hot_replica<K4>(p) + (size_t)((uint32_t)(h >> 20) & (kHotSlots - 1u)) * SlotLayout<K4>::BYTES
+                                 : p.slots + (size_t)((uint32_t)(h >> 32) & p.slot_mask) * SlotLayout<K4>::BYTES;
+                if (K4 == 4) ld_relaxed_u128(s, pr.c[0], pr.c[HI]);
+                else pr.c[0] = ld_relaxed_u64(s);
+                pr.slot = s;
                 pr.h = h;
                 pr.b = b;
                 pr.pk = pk;
@@ -441,24 +436,17 @@ __device__ __forceinline__ uint32_t aggregate_begin(const SubmitParams &p, const
     return (uint32_t)h;
 }
 
-// The key sits in the first slot of its probe sequence that no other key holds: slot 0 if it matches; slot 1 if slot
-// 0 holds another key and slot 1 matches.  Everything else (an empty slot to claim, a longer sequence) is the
-// ordinary probe loop from the start.
+// The slot holds the key: the three reductions.  Empty, or another key: the ordinary probe loop from the start (CAS
+// claim included).
 template <int KW>
 __device__ __forceinline__ void aggregate_finish(const SubmitParams &p, Probe<KW> &pr)
 {
-    if (!pr.table) return;
+    if (!pr.slot) return;
     constexpr int HI = Probe<KW>::KEY64 - 1;
-    bool same0 = pr.c[0][0] == pr.k[0], same1 = pr.c[1][0] == pr.k[0];
-    bool empty0 = pr.c[0][0] == ~0ull;
-    if (KW == 4) {
-        same0 = same0 && pr.c[0][HI] == pr.k[HI];
-        same1 = same1 && pr.c[1][HI] == pr.k[HI];
-        empty0 = (pr.c[0][0] & pr.c[0][HI]) == ~0ull;
-    }
-    if (same0 || (same1 && !empty0)) {
-        const uint32_t slot = same0 ? pr.slot : ((pr.slot + 1u) & pr.mask);
-        slot_add(pr.table + (size_t)slot * SlotLayout<KW>::BYTES + SlotLayout<KW>::VAL_OFF, pr.b, pr.pk, 1ull);
+    bool same = pr.c[0] == pr.k[0];
+    if (KW == 4) same = same && pr.c[HI] == pr.k[HI];
+    if (same) {
+        slot_add(pr.slot + SlotLayout<KW>::VAL_OFF, pr.b, pr.pk, 1ull);
     } else {
         uint32_t key[KW];
         key[0] = (uint32_t)pr.k[0];
@@ -468,10 +456,10 @@ __device__ __forceinline__ void aggregate_finish(const SubmitParams &p, Probe<KW
             key[KW == 4 ? 3 : 0] = (uint32_t)(pr.k[HI] >> 32);
         }
         bool done = false;
-        if (pr.hot) done = hot_add<KW>(pr.table, key, pr.h, pr.b, pr.pk);
+        if (pr.hot) done = hot_add<KW>(hot_replica<KW>(p), key, pr.h, pr.b, pr.pk);
         if (!done) table_add<KW>(p, key, pr.h, pr.b, pr.pk, 1ull);
     }
-    pr.table = nullptr;
+    pr.slot = nullptr;
 }
 
 // ---- tile staging: one bulk-async copy per tile ----------------------------------------------
@@ -511,43 +499,39 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, ui
                  : "memory");
 }
 
-struct TileInfo {
-    uint32_t r0, n;   // first record, record count
-    uint32_t b0;      // stream byte of the tile's first record
-    uint32_t a0;      // b0 rounded down to 16: stream byte of shared-memory byte 0
-    uint32_t s_end;   // stream byte one past the staged range (a0 if nothing is staged)
-};
-
-// Stage as much of the byte span of records [r0, r0+n) as fits into shared memory.
-// Records that end beyond s_end (oversized tiles, out-of-order offsets) are parsed
-// from global memory instead.  Stream positions fit 32 bits (offsets are u32).
-__device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t tile, uint8_t *smem)
+// Staged span of a tile whose records occupy stream bytes [b0, b1): as much as fits the buffer, starting at b0
+// rounded down to 16 (the bulk copy's alignment).  Returns the stream byte one past the staged range (= b0 & ~15
+// when nothing can be staged: insane bounds).  Records that end beyond it (oversized tiles, out-of-order offsets)
+// are parsed from global memory instead.  Stream positions fit 32 bits (offsets are u32).
+__device__ __forceinline__ uint32_t tile_staged_end(const SubmitParams &p, uint32_t b0, uint32_t b1)
 {
-    TileInfo t;
-    t.r0 = tile * p.tile_records;
-    t.n = min(p.tile_records, p.n_records - t.r0);
-    t.b0 = __ldg(p.offsets + t.r0);
-    const uint32_t b1 = __ldg(p.offsets + t.r0 + t.n);
-    t.a0 = t.b0 & ~15u;
-    const uint32_t base = (uint32_t)p.base, end = base + (uint32_t)p.len;
-    const bool sane = t.b0 <= b1 && t.b0 >= base && b1 <= end;
-    const uint32_t nbytes = sane ? min((b1 - t.a0 + 15u) & ~15u, p.tile_bytes) : 0u;
-    t.s_end = t.a0 + nbytes;
-    const uint32_t bar = smem_u32(smem + p.tile_bytes + kTilePad);
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t a0 = b0 & ~15u, base = (uint32_t)p.base, end = base + (uint32_t)p.len;
+    const bool sane = b0 <= b1 && b0 >= base && b1 <= end;
+    return a0 + (sane ? min((b1 - a0 + 15u) & ~15u, p.tile_bytes) : 0u);
+}
+
+// One thread: stage tile t (records' bytes [b0, b1)) into a buffer -- the bytes AND the tile's slice of the offsets
+// array (n+1 words), two bulk copies completing on the buffer's barrier.  The copies move whole 16-byte units; the odd
+// tail of the offsets slice (one word for a full tile of 256) is stored by this thread before it arms the barrier.
+__device__ __forceinline__ void tile_issue(const SubmitParams &p, uint32_t t, uint32_t b0, uint32_t b1, uint32_t buf, uint32_t *soff,
+                                           uint2 *bounds, uint32_t bar)
+{
+    const uint32_t r0 = t * p.tile_records, n = min(p.tile_records, p.n_records - r0);
+    const uint32_t *src = p.offsets + r0;
+    const uint32_t s_end = tile_staged_end(p, b0, b1), a0 = b0 & ~15u, nbytes = s_end - a0;
+    *bounds = make_uint2(b0, s_end);
+    const uint32_t bulk_words = p.offsets_aligned ? ((n + 1u) & ~3u) : 0u;
+    for (uint32_t i = bulk_words; i < n; i++) soff[i] = __ldg(src + i);
+    soff[n] = b1;
+    // the buffer's last readers used ordinary loads; the copies write through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (nbytes + bulk_words) {
+        mbar_expect_tx(bar, nbytes + bulk_words * 4u);
+        if (nbytes) bulk_load(buf, p.buf + (a0 - (uint32_t)p.base), nbytes, bar);
+        if (bulk_words) bulk_load(smem_u32(soff), src, bulk_words * 4u, bar);
+    } else {
+        mbar_arrive(bar);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (nbytes) {
-            mbar_expect_tx(bar, nbytes);
-            bulk_load(smem_u32(smem), p.buf + (t.a0 - base), nbytes, bar);
-        } else {
-            mbar_arrive(bar);
-        }
-    }
-    return t;
 }
 
 // ---- consumers ----------------------------------------------------------------------------------
@@ -579,14 +563,6 @@ struct AggConsumer {
     static constexpr int KW = KeyTraits<MODE>::KW;
     static constexpr int PKW = KW <= 4 ? KW : 1;  // layout of the in-flight probe (unused for wide keys)
     static constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
-#ifndef FA_AGG_NR
-#define FA_AGG_NR 1
-#endif
-    static constexpr int NR = KW <= 4 ? FA_AGG_NR : 1;   // records parsed side by side by one thread
-#ifndef FA_AGG_MIN_BLOCKS
-#define FA_AGG_MIN_BLOCKS 8
-#endif
-    static constexpr int MIN_BLOCKS = KW <= 4 ? FA_AGG_MIN_BLOCKS : 4;   // CTAs of 256 threads' worth of records per SM (32 / 64 registers)
     static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     static constexpr bool PERMUTE = true;                // nothing is stored per record: lanes may take any record
     struct Item {
@@ -594,7 +570,7 @@ struct AggConsumer {
         bool have;
     };
     typedef Probe<PKW> State;
-    static __device__ __forceinline__ void state_clear(State &st) { st.table = nullptr; }
+    static __device__ __forceinline__ void state_clear(State &st) { st.slot = nullptr; }
     static __device__ __forceinline__ void item_clear(Item &it)
     {
         it.h32 = 0;
@@ -642,8 +618,6 @@ __device__ __forceinline__ uint4 addr_bytes(const uint32_t be[4])
 
 struct ColConsumer {
     static constexpr uint32_t NEED = F_ALL;
-    static constexpr int NR = 1;            // all 16 fields live: one record per thread
-    static constexpr int MIN_BLOCKS = 4;    // 64 registers
     static constexpr bool PERMUTE = false;  // column stores stay coalesced: lane i writes row r0+i
     struct Item {};
     struct State {};
@@ -744,88 +718,129 @@ __device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad
     }
 }
 
-// Which records of the tile does a thread parse?  Slot v of the tile's 256 parse slots is slot v / (256 / NR) of thread
-// v % (256 / NR).  Lanes of a warp read their records from shared memory in lock step, so the bank pattern is set by the
-// byte distance between the records of neighbouring lanes.  With consecutive records and near-constant record sizes
-// that distance can resonate with the 32 x 4-byte banks (measured: 86-byte records = 21.5 words, 3 lanes apart =
-// 64.5 words -> every third lane on one bank).  Each group of d = 2^shift 32-slot rows therefore shares a run of
-// 32*d records, neighbouring lanes taking records d apart; d is chosen per batch from its mean record size
-// (pick_lane_stride, host side).  A bijection on [0, kTileRecords).
-__device__ __forceinline__ uint32_t record_of_slot(uint32_t v, uint32_t shift)
+// Which record of the tile does this thread parse?  Lanes of a warp read their records from shared memory in
+// lock step, so the bank pattern is set by the byte distance between the records of neighbouring lanes.  With
+// consecutive records and near-constant record sizes that distance can resonate with the 32 x 4-byte banks
+// (measured: 86-byte records = 21.5 words, 3 lanes apart = 64.5 words -> every third lane on one bank).  Each
+// group of d = 2^shift warps therefore shares a run of 32*d records, neighbouring lanes taking records d apart;
+// d is chosen per batch from its mean record size (pick_lane_stride, host side).  A bijection on [0, kThreads).
+__device__ __forceinline__ uint32_t record_of_thread(uint32_t shift)
 {
-    const uint32_t lane = v & 31u, row = v >> 5;
-    return ((row >> shift) << (5u + shift)) + (lane << shift) + (row & ((1u << shift) - 1u));
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    return ((warp >> shift) << (5u + shift)) + (lane << shift) + (warp & ((1u << shift) - 1u));
 }
 
-// ---- the tile kernel: decode (+ consume) one tile per CTA, kRecordsPerThread records per thread ----------------
+// ---- the stream kernel: decode (+ consume) tiles blockIdx.x, blockIdx.x + gridDim.x, ... ---------------------
+//
+// Shared memory: two tile buffers of tile_bytes + kTilePad each, two offsets slices of kStreamOffBytes, then
+// {full[2] mbarriers, readers_done[2], bounds[2], next_bounds[2][2]}.
 
 template <class Consumer>
-__global__ void __launch_bounds__(kTileRecords / Consumer::NR, Consumer::MIN_BLOCKS * Consumer::NR) k_tile(const __grid_constant__ TileParams tp)
+__global__ void __launch_bounds__(kThreads, kStreamBlocksPerSM) k_stream(const __grid_constant__ TileParams tp)
 {
-    constexpr int NR = Consumer::NR, THREADS = kTileRecords / NR;
     extern __shared__ __align__(128) uint8_t smem[];
     const SubmitParams &p = tp.p;
-    const TileInfo t = stage_tile(p, blockIdx.x, smem);
-    const bool hot = Consumer::want_hot(p);  // uniform over the grid; the load overlaps the tile copy
-    uint32_t bad = 0, nokey = 0, slow = 0;
-    uint32_t r[NR], o0[NR], o1[NR];
-    bool active[NR];
-#pragma unroll
-    for (int q = 0; q < NR; q++) {
-        uint32_t in_tile = threadIdx.x + q * THREADS;
-        // full tiles only (the mapping is a bijection on [0, kTileRecords)); short tails keep the identity
-        if (Consumer::PERMUTE && p.lane_shift && t.n == (uint32_t)kTileRecords) in_tile = record_of_slot(in_tile, p.lane_shift);
-        active[q] = in_tile < t.n;
-        r[q] = t.r0 + in_tile;
-        o0[q] = o1[q] = 0;
-        if (active[q]) {  // in flight while the bulk copy lands
-            o0[q] = __ldg(p.offsets + r[q]);
-            o1[q] = __ldg(p.offsets + r[q] + 1);
+    const uint32_t buf_stride = p.tile_bytes + kTilePad;
+    uint8_t *offs_area = smem + 2u * buf_stride;                             // two offsets slices of kStreamOffBytes
+    uint8_t *ctl = offs_area + 2u * kStreamOffBytes;
+    const uint32_t bar0 = smem_u32(ctl);                                     // full[b] at bar0 + 8 b
+    unsigned int *readers_done = reinterpret_cast<unsigned int *>(ctl + 16); // [2]
+    uint2 *bounds = reinterpret_cast<uint2 *>(ctl + 32);                     // [2]: {b0, s_end} of the tile in buffer b
+    volatile uint32_t *next_bounds = reinterpret_cast<volatile uint32_t *>(ctl + 48);  // [2][2]: byte bounds of the tile to stage next in buffer b
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_tiles = p.n_tiles, step = gridDim.x;
+    const uint32_t n_warps = kThreads / 32;
+
+    // byte bounds of tile t's records: which = 0 the first record's start, 1 the last record's end
+    auto tile_bound = [&](uint32_t t, uint32_t which) {
+        const uint32_t r0 = t * p.tile_records, n = min(p.tile_records, p.n_records - r0);
+        return __ldg(p.offsets + r0 + (which ? n : 0u));
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        readers_done[0] = readers_done[1] = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint32_t k = 0; k < 2u; k++) {  // the first two tiles of this CTA
+            const uint32_t t = blockIdx.x + k * step;
+            if (t < n_tiles)
+                tile_issue(p, t, tile_bound(t, 0), tile_bound(t, 1), smem0 + k * buf_stride,
+                           reinterpret_cast<uint32_t *>(offs_area + k * kStreamOffBytes), bounds + k, bar0 + 8u * k);
         }
     }
-    mbar_wait(smem_u32(smem + p.tile_bytes + kTilePad), 0);
+    __syncthreads();
 
-    // every thread walks the field list for its NR records together (slots without a staged record walk an empty span);
-    // cursors are absolute shared-window addresses (the buffer is 16-byte aligned, so alignment arithmetic is unchanged)
-    const uint32_t buf = smem_u32(smem);
-    bool from_tile[NR], fast[NR];
-    uint32_t pos[NR], end[NR], p0[NR];
-    Flow f[NR];
-#pragma unroll
-    for (int q = 0; q < NR; q++) {
-        from_tile[q] = active[q] && o0[q] >= t.b0 && o0[q] <= o1[q] && o1[q] <= t.s_end;
-        p0[q] = pos[q] = buf + (from_tile[q] ? o0[q] - t.a0 : 0u);
-        end[q] = buf + (from_tile[q] ? o1[q] - t.a0 : 0u);
-        flow_reset(f[q]);
-    }
-    SmemSrc s;
-    s.base = 0u;
-    decode_records_shape<Consumer::NEED, NR>(tp.shape, s, pos, end, p.framed != 0, f, fast);
+    const bool hot = Consumer::want_hot(p);  // uniform over the grid
+    const bool framed = p.framed != 0;
+    uint32_t bad = 0, nokey = 0, slow = 0;
+    uint32_t in_tile = threadIdx.x;
+    if (Consumer::PERMUTE && p.lane_shift) in_tile = record_of_thread(p.lane_shift);
+    typename Consumer::State state;  // the previous tile's record: its first probe is in flight during this tile's parse
+    Consumer::state_clear(state);
 
-    typename Consumer::Item item[NR];
-    typename Consumer::State state[NR];
-#pragma unroll
-    for (int q = 0; q < NR; q++) {
-        Consumer::item_clear(item[q]);
-        Consumer::state_clear(state[q]);
-        if (fast[q]) Consumer::begin(tp, r[q], true, f[q], bad, nokey, hot, item[q], state[q]);  // both probes in flight together
-    }
-#pragma unroll
-    for (int q = 0; q < NR; q++) {
-        Consumer::finish(tp, state[q]);
-        if (!fast[q] && active[q]) {  // not decided by the fast path: the order-agnostic decoder, consumed on the spot
+    uint32_t k = 0;
+#pragma unroll 1
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += step, k++) {
+        const uint32_t b = k & 1u;
+        const uint32_t r0 = t * p.tile_records, n = min(p.tile_records, p.n_records - r0);
+        // short tails keep the identity mapping (the permutation is a bijection on full tiles only)
+        const uint32_t mine = n == (uint32_t)kThreads ? in_tile : threadIdx.x;
+        const bool active = mine < n;
+        const uint32_t r = r0 + mine;
+        const uint32_t *soff = reinterpret_cast<const uint32_t *>(offs_area + b * kStreamOffBytes);
+        // warp 0 fetches the byte bounds of the tile that will follow this one in buffer b (lane 0: begin, lane 1: end);
+        // they travel through shared memory to whichever warp re-arms the buffer, a whole parse later
+        const bool refill = t + 2u * step < n_tiles;
+        uint32_t nbound = 0;
+        if (refill && threadIdx.x < 2u) nbound = tile_bound(t + 2u * step, threadIdx.x);
+
+        mbar_wait(bar0 + 8u * b, (k >> 1) & 1u);
+        const uint2 bb = bounds[b];  // {b0, s_end}
+        const uint32_t o0 = active ? soff[mine] : 0u, o1 = active ? soff[mine + 1u] : 0u;
+        const uint32_t buf = smem0 + b * buf_stride, a0 = bb.x & ~15u;
+        typename Consumer::Item item;
+        Consumer::item_clear(item);
+        // every lane walks the field list (lanes without a staged record walk an empty span); cursors are absolute
+        // shared-window addresses (the buffers are 16-byte aligned, so alignment arithmetic is unchanged)
+        const bool from_tile = active && o0 >= bb.x && o0 <= o1 && o1 <= bb.y;
+        const uint32_t p0 = buf + (from_tile ? o0 - a0 : 0u), p1 = buf + (from_tile ? o1 - a0 : 0u);
+        Flow f;
+        flow_reset(f);
+        SmemSrc s;
+        s.base = 0u;
+        const bool fast = decode_record_shape<Consumer::NEED>(tp.shape, s, p0, p1, framed, f) && from_tile;
+        if (!fast && active) {  // parsed by the order-agnostic decoder and consumed on the spot
             uint32_t res;
-            if (from_tile[q]) {
+            if (from_tile) {
                 slow++;
-                res = record_from_tile<Consumer>(tp, r[q], 0u, p0[q], end[q], hot);
+                res = record_from_tile<Consumer>(tp, r, 0u, p0, p1, hot);
             } else {
-                res = record_from_global<Consumer>(tp, r[q], o0[q], o1[q]);
+                res = record_from_global<Consumer>(tp, r, o0, o1);
             }
             bad += res & 1u;
             nokey += res >> 1;
         }
-        Consumer::sample_repeats(p, blockIdx.x, item[q]);
+        // this warp is done with buffer b: count it (the answer -- am I the last? -- is looked at after the table work)
+        if (refill && threadIdx.x < 2u) next_bounds[2u * b + threadIdx.x] = nbound;
+        __syncwarp();
+        unsigned int seen = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            seen = atomicAdd(&readers_done[b], 1u);
+        }
+        Consumer::finish(tp, state);  // the previous tile's record: its probe has had a whole parse to come back
+        if (fast) Consumer::begin(tp, r, true, f, bad, nokey, hot, item, state);
+        Consumer::sample_repeats(p, t, item);
+        // buffer b is free once all warps are past it; the last one re-arms it with tile k+2 of this CTA
+        if (lane == 0 && seen == n_warps - 1u) {
+            readers_done[b] = 0u;
+            if (refill)
+                tile_issue(p, t + 2u * step, next_bounds[2u * b], next_bounds[2u * b + 1u], buf,
+                           reinterpret_cast<uint32_t *>(offs_area + b * kStreamOffBytes), bounds + b, bar0 + 8u * b);
+        }
     }
+    Consumer::finish(tp, state);
     flush_counts(p, bad, nokey, slow);
 }
 
@@ -922,7 +937,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
         }
         bool have;
         Probe<(KeyTraits<MODE>::KW <= 4 ? KeyTraits<MODE>::KW : 1)> pr;
-        pr.table = nullptr;
+        pr.slot = nullptr;
         aggregate_begin<MODE>(p, f, nokey, false, have, pr);
         aggregate_finish(p, pr);
     }
@@ -971,20 +986,24 @@ __global__ void __launch_bounds__(256) k_merge_hot(const SubmitParams p, uint32_
     }
 }
 
+// is_side: the reserved slot behind the table (the all-ones key); it is occupied iff side_claimed (counters->side_state,
+// which is what n_groups counted) -- its count alone would miss a key whose merged count is 0.
 template <int KW>
-__device__ __forceinline__ bool slot_read(const uint8_t *s, bool is_side, uint32_t *key)
+__device__ __forceinline__ bool slot_read(const uint8_t *s, bool is_side, bool side_claimed, uint32_t *key)
 {
     if (KW <= 2) {
         const unsigned long long k = *reinterpret_cast<const unsigned long long *>(s);
         key[0] = (uint32_t)k;
         if (KW == 2) key[1] = (uint32_t)(k >> 32);
         const unsigned long long cnt = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF)[2];
-        return is_side ? cnt != 0 : k != ~0ull;
+        (void)cnt;
+        return is_side ? side_claimed : k != ~0ull;
     } else if (KW == 4) {
         const unsigned long long lo = reinterpret_cast<const unsigned long long *>(s)[0], hi = reinterpret_cast<const unsigned long long *>(s)[1];
         key[0] = (uint32_t)lo; key[1] = (uint32_t)(lo >> 32); key[2] = (uint32_t)hi; key[3] = (uint32_t)(hi >> 32);
         const unsigned long long cnt = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF)[2];
-        return is_side ? cnt != 0 : (lo & hi) != ~0ull;
+        (void)cnt;
+        return is_side ? side_claimed : (lo & hi) != ~0ull;
     } else {
         const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
 #pragma unroll
@@ -1000,7 +1019,7 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsi
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
         uint32_t key[KW];
-        if (!slot_read<KW>(s, i == n_slots - 1, key)) continue;
+        if (!slot_read<KW>(s, i == n_slots - 1, counters->side_state != 0u, key)) continue;
         if (i == n_slots - 1) {  // the side slot holds the all-ones key
 #pragma unroll
             for (int k = 0; k < KW; k++) key[k] = 0xFFFFFFFFu;
@@ -1048,7 +1067,7 @@ __global__ void __launch_bounds__(256) k_estimate(const uint8_t *slots, unsigned
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
         uint32_t key[KW];
-        if (!slot_read<KW>(s, i == n_slots - 1, key)) continue;
+        if (!slot_read<KW>(s, i == n_slots - 1, counters->side_state != 0u, key)) continue;
         if (i == n_slots - 1) {
 #pragma unroll
             for (int k = 0; k < KW; k++) key[k] = 0xFFFFFFFFu;

@@ -57,7 +57,7 @@ class FaConfig(C.Structure):
 
 
 class FaStats(C.Structure):
-    _fields_ = [(k, C.c_uint64) for k in ("n_records", "n_bad", "n_nokey", "n_dropped", "n_groups", "n_submits", "bytes_in", "n_kernels", "n_slow")]
+    _fields_ = [(k, C.c_uint64) for k in ("n_records", "n_bad", "n_nokey", "n_dropped", "n_groups", "n_submits", "bytes_in", "n_kernels", "n_slow", "gpu_busy_us")]
 
 
 class FaMockerConfig(C.Structure):

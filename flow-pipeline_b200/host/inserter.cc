@@ -66,10 +66,12 @@ struct Flags {
     int Devices = 1;                      // -gpus: partition p runs on GPU p mod gpus
     std::string Format = "tsv";           // -format tsv | rowbinary: Clickhouse RowBinary of the flows_5m schema (create.sh:70-87)
     std::string Sink = "flows5m";         // -sink flows5m: roll-up rows (create.sh:70-87); rows: the inserter's own
-                                          //       14-column row per flow (inserter.go:51-66,142-157)
+                                          //       14-column row per flow (inserter.go:51-66,142-157), TSV as Go would print it;
+                                          //       copy: the same rows as a Postgres `COPY flows (...) FROM stdin` script
     bool FlushBox = false;                // -flush.box: the closing flush is ONE exact roll-up over every partition (fa_flush_box)
     bool DryRun = false;                  // -dry-run: walk the claims and fill slabs, no GPU, no aggregates
     bool Metrics = false;                 // -metrics: serve -metrics.addr (off by default in this mirror)
+    double Linger = 0;                    // -linger: keep serving metrics this long after the claims are drained (or until SIGTERM)
 };
 
 static double parse_duration(const std::string &s)
@@ -133,6 +135,7 @@ static bool parse_flags(int argc, char **argv, Flags &f)
         else if (a == "dry-run") f.DryRun = true;
         else if (a == "flush.box") f.FlushBox = true;
         else if (a == "metrics") f.Metrics = true;
+        else if (a == "linger") f.Linger = parse_duration(val());
         else {
             fprintf(stderr, "flag provided but not defined: -%s\n", a.c_str());
             return false;
@@ -238,6 +241,18 @@ struct FileClaim : ConsumerGroupClaim {
     }
 };
 
+// "?" + hexString(ip): what net.IP.String() prints for a length that is neither 4 nor 16
+static std::string ip_string_hex(const uint8_t *p, size_t len)
+{
+    std::string o = "?";
+    static const char hx[] = "0123456789abcdef";
+    for (size_t i = 0; i < len; i++) {
+        o += hx[p[i] >> 4];
+        o += hx[p[i] & 15];
+    }
+    return o;
+}
+
 // ---- net.IP(b).String() with the "<nil>" -> "0.0.0.0" patch of inserter.go:131-140 ------------------
 static std::string ip_string(const uint8_t *p, size_t len)
 {
@@ -254,15 +269,7 @@ static std::string ip_string(const uint8_t *p, size_t len)
         snprintf(buf, sizeof buf, "%u.%u.%u.%u", p4[0], p4[1], p4[2], p4[3]);
         return buf;
     }
-    if (len != 16) {  // "?" + hexString(ip)
-        std::string o = "?";
-        static const char hx[] = "0123456789abcdef";
-        for (size_t i = 0; i < len; i++) {
-            o += hx[p[i] >> 4];
-            o += hx[p[i] & 15];
-        }
-        return o;
-    }
+    if (len != 16) return ip_string_hex(p, len);
     int e0 = -1, e1 = -1;  // longest run of zero groups, leftmost on ties, at least two groups
     for (int i = 0; i < 16; i += 2) {
         int j = i;
@@ -291,8 +298,10 @@ static std::string ip_string(const uint8_t *p, size_t len)
 
 // ---- state (inserter.go:75-88) --------------------------------------------------------------------
 static const char *kKeyNames[] = {"flows5m", "aspair", "srcaddr", "dstaddr", "5tuple", "srcport", "dstport"};
-static std::atomic<uint64_t> g_inserts{0};  // the insert_count counter (inserter.go:44-49)
+// insert_count (inserter.go:44-49, "Inserts made to Postgres", never incremented upstream): one per flow that decoded and
+// went to the sink or the roll-up = g_records - g_bad, refreshed wherever the context's counters are read
 static std::atomic<uint64_t> g_rows{0}, g_bad{0}, g_flushes{0};  // roll-up rows written, undecodable messages, flushes
+static std::atomic<uint64_t> g_records{0}, g_gpu_busy_us{0};    // messages handed to the GPU; device time of its kernels
 static std::atomic<bool> g_stop{false};
 
 struct PartitionState {  // what one ConsumeClaim goroutine owns
@@ -302,7 +311,7 @@ struct PartitionState {  // what one ConsumeClaim goroutine owns
     uint32_t *offs = nullptr;
     size_t slab_cap = 0, rec_cap = 0, fill = 0, nrec = 0;
     std::vector<ConsumerMessage> pending;  // marked once their slab is submitted
-    uint64_t bad_seen = 0;                 // fa_stats.n_bad already added to the metrics
+    uint64_t bad_seen = 0, records_seen = 0, busy_seen = 0;  // fa_stats figures already added to the metrics
 };
 
 struct state {
@@ -314,12 +323,21 @@ struct state {
     int key_mode = 0;
     uint64_t rows_written = 0, bad = 0;
 
+    bool per_flow_sink() const { return fl.Sink == "rows" || fl.Sink == "copy"; }
+
     int Setup(ConsumerGroupSession &)
     {
         ready = true;
+        if (fl.Sink == "copy")  // the insert of inserter.go:99-106, as one COPY instead of one INSERT per flow
+            fprintf(out, "COPY flows (date_inserted, time_flow, type, sampling_rate, src_ip, dst_ip, bytes, packets, src_port, dst_port, etype, "
+                         "proto, src_as, dst_as) FROM stdin;\n");
         return 0;
     }
-    int Cleanup(ConsumerGroupSession &) { return 0; }
+    int Cleanup(ConsumerGroupSession &)
+    {
+        if (fl.Sink == "copy") fprintf(out, "\\.\n");  // end-of-data marker of COPY ... FROM stdin
+        return 0;
+    }
 
     void acquire_slab(PartitionState &ps)
     {
@@ -354,10 +372,9 @@ struct state {
                 exit(1);
             }
         }
-        if (!fl.DryRun && fl.Sink == "rows") write_flow_rows(ps);
+        if (!fl.DryRun && per_flow_sink()) write_flow_rows(ps);
         for (const ConsumerMessage &m : ps.pending) sess.MarkMessage(m);  // after the hand-over, not before (inserter.go:188)
         ps.pending.clear();
-        g_inserts += ps.nrec;
         ps.slot ^= 1;
         acquire_slab(ps);
     }
@@ -390,7 +407,7 @@ struct state {
     {
         logf(2, "Processed %ld records in the last iteration.", msgCount.exchange(0));
         submit_slab(ps, sess);
-        if (fl.DryRun || fl.Sink == "rows") return true;
+        if (fl.DryRun || per_flow_sink()) return true;
         if (closing && fl.FlushBox) return true;  // main() merges every partition's table in one fa_flush_box
         size_t n = 0;
         std::vector<fa_row> rows(1 << 16);
@@ -408,6 +425,10 @@ struct state {
         std::lock_guard<std::mutex> lk(out_mu);
         g_bad += st.n_bad - ps.bad_seen;
         ps.bad_seen = st.n_bad;
+        g_records += st.n_records - ps.records_seen;
+        ps.records_seen = st.n_records;
+        g_gpu_busy_us += st.gpu_busy_us - ps.busy_seen;
+        ps.busy_seen = st.gpu_busy_us;
         g_flushes++;
         bad = st.n_bad;
         for (size_t i = 0; i < n; i++) write_row(rows[i]);
@@ -442,8 +463,29 @@ struct state {
                 bad++;
                 continue;
             }
-            // an address longer than 16 bytes is kept as its first 16 (FixedString(16), create.sh:15-16)
-            const std::string s_ip = ip_string(&sa[i * 16], sal[i] > 16 ? 16 : sal[i]), d_ip = ip_string(&da[i * 16], dal[i] > 16 ? 16 : dal[i]);
+            // net.IP.String() of a value that is neither 4 nor 16 bytes long is "?" + hex of the whole value (inserter.go:131-140).
+            // The columns keep the first 16 bytes and the true length (FixedString(16), create.sh:15-16), so a longer address
+            // prints as "?" + hex of those 16 bytes + ".." (the tail is not kept anywhere downstream either).
+            auto addr_text = [](const uint8_t *p, unsigned len) {
+                return len > 16 ? ip_string_hex(p, 16) + ".." : ip_string(p, len);
+            };
+            const std::string s_ip = addr_text(&sa[i * 16], sal[i]), d_ip = addr_text(&da[i * 16], dal[i]);
+            if (fl.Sink == "copy") {
+                // Postgres COPY text format: tab-separated literals.  date_inserted is NOW() upstream (a SQL expression,
+                // inserter.go:142): its value at the moment of the copy; time_flow = time.Unix(TimeFlowStart, 0) (:143), UTC.
+                // The address texts hold only [0-9a-f.:?], nothing COPY would need escaped.
+                char now_s[40], tf_s[40];
+                const time_t now_t = time(nullptr), tf_t = (time_t)tfs[i];
+                struct tm tmv;
+                gmtime_r(&now_t, &tmv);
+                strftime(now_s, sizeof now_s, "%Y-%m-%d %H:%M:%S+00", &tmv);
+                gmtime_r(&tf_t, &tmv);
+                strftime(tf_s, sizeof tf_s, "%Y-%m-%d %H:%M:%S+00", &tmv);
+                fprintf(out, "%s\t%s\t%d\t%" PRIu64 "\t%s\t%s\t%" PRIu64 "\t%" PRIu64 "\t%u\t%u\t%u\t%u\t%u\t%u\n", now_s, tf_s, (int32_t)ty[i],
+                        sr[i], s_ip.c_str(), d_ip.c_str(), by[i], pk[i], sp[i], dp[i], et[i], pr[i], sas[i], das[i]);
+                rows_written++;
+                continue;
+            }
             fprintf(out, "NOW()\t%" PRIu64 "\t%d\t%" PRIu64 "\t%s\t%s\t%" PRIu64 "\t%" PRIu64 "\t%u\t%u\t%u\t%u\t%u\t%u\n", tfs[i], (int32_t)ty[i], sr[i],
                     s_ip.c_str(), d_ip.c_str(), by[i], pk[i], sp[i], dp[i], et[i], pr[i], sas[i], das[i]);
             rows_written++;
@@ -578,15 +620,20 @@ static void metricsHTTP(const Flags &fl)
         char req[1024];
         ssize_t n = read(cfd, req, sizeof req - 1);
         (void)n;
-        char body[1024], resp[1280];
+        char body[2048], resp[2400];
         int bl = snprintf(body, sizeof body,
                           "# HELP insert_count Inserts made to Postgres.\n# TYPE insert_count counter\ninsert_count %" PRIu64 "\n"
                           "# HELP flowagg_rollup_rows_total Aggregate rows written to the sink.\n# TYPE flowagg_rollup_rows_total counter\n"
                           "flowagg_rollup_rows_total %" PRIu64 "\n"
                           "# HELP flowagg_bad_records_total Messages proto.Unmarshal would reject (skipped, inserter.go:125).\n"
                           "# TYPE flowagg_bad_records_total counter\nflowagg_bad_records_total %" PRIu64 "\n"
-                          "# HELP flowagg_flushes_total Roll-up flushes.\n# TYPE flowagg_flushes_total counter\nflowagg_flushes_total %" PRIu64 "\n",
-                          g_inserts.load(), g_rows.load(), g_bad.load(), g_flushes.load());
+                          "# HELP flowagg_flushes_total Roll-up flushes.\n# TYPE flowagg_flushes_total counter\nflowagg_flushes_total %" PRIu64 "\n"
+                          "# HELP flowagg_records_total Kafka messages decoded on the GPU.\n# TYPE flowagg_records_total counter\n"
+                          "flowagg_records_total %" PRIu64 "\n"
+                          "# HELP flowagg_gpu_busy_seconds_total Device time of the decode/aggregate kernels (CUDA events).\n"
+                          "# TYPE flowagg_gpu_busy_seconds_total counter\nflowagg_gpu_busy_seconds_total %.6f\n",
+                          g_records.load() - g_bad.load(), g_rows.load(), g_bad.load(), g_flushes.load(), g_records.load(),
+                          (double)g_gpu_busy_us.load() / 1e6);
         int rl = snprintf(resp, sizeof resp, "HTTP/1.1 200 OK\r\nContent-Type: text/plain; version=0.0.4\r\nContent-Length: %d\r\n\r\n%s", bl, body);
         if (write(cfd, resp, (size_t)rl) < 0) {}
         close(cfd);
@@ -629,7 +676,7 @@ int main(int argc, char **argv)
             cfg.key_mode = (uint32_t)s.key_mode;
             cfg.max_batch_bytes = 64u << 20;
             cfg.max_batch_records = 1u << 20;
-            if (s.fl.Sink == "rows") cfg.flags = FA_CFG_COLUMNS | FA_CFG_NO_AGGREGATE;  // kernel 1 alone
+            if (s.per_flow_sink()) cfg.flags = FA_CFG_COLUMNS | FA_CFG_NO_AGGREGATE;  // kernel 1 alone
             int rc = fa_create(&cfg, &parts[p].ctx);
             if (rc) {
                 logf(0, "fa_create: %s (%s)", fa_strerror(rc), parts[p].ctx ? fa_last_error(parts[p].ctx) : "");
@@ -641,12 +688,28 @@ int main(int argc, char **argv)
     std::vector<std::thread> th;
     for (size_t p = 0; p < np; p++) th.emplace_back([&, p] { s.ConsumeClaim(sess, *claims[p], parts[p]); });
     for (auto &t : th) t.join();
-    if (s.fl.FlushBox && !s.fl.DryRun && s.fl.Sink != "rows") s.flush_box(parts);
+    if (s.fl.FlushBox && !s.fl.DryRun && !s.per_flow_sink()) s.flush_box(parts);
     s.Cleanup(sess);
     uint64_t total = 0;
     for (auto &kv : sess.marked) total += (uint64_t)kv.second;
     logf(2, "done: %" PRIu64 " messages marked over %zu partitions, %" PRIu64 " rows written, %" PRIu64 " undecodable", total, np, s.rows_written,
          s.bad);
+    for (auto &ps : parts) {
+        if (!ps.ctx) continue;
+        fa_stats st;
+        if (fa_stats_get(ps.ctx, &st) == FA_OK) {  // final figures for the metrics endpoint
+            g_bad += st.n_bad - ps.bad_seen;
+            ps.bad_seen = st.n_bad;
+            g_records += st.n_records - ps.records_seen;
+            ps.records_seen = st.n_records;
+            g_gpu_busy_us += st.gpu_busy_us - ps.busy_seen;
+            ps.busy_seen = st.gpu_busy_us;
+        }
+    }
+    if (s.fl.Metrics && s.fl.Linger > 0) {  // a scraper gets to see the final counters
+        const auto until = std::chrono::steady_clock::now() + std::chrono::duration<double>(s.fl.Linger);
+        while (!g_stop && std::chrono::steady_clock::now() < until) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    }
     for (auto &ps : parts)
         if (ps.ctx) fa_destroy(ps.ctx);
     g_stop = true;

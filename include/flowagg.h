@@ -116,6 +116,8 @@ typedef struct fa_stats {
     uint64_t n_kernels;  /* launches of the library's own CUDA kernels (all kinds) */
     uint64_t n_slow;     /* records the decoder's lock-step fast path did not decide (parsed by the
                             order-agnostic decoder instead; same result, ~2x the instructions)     */
+    uint64_t gpu_busy_us; /* device time of the decode/aggregate kernels so far (CUDA events around
+                             every launch; what a GPU-busy gauge divides by wall time)            */
 } fa_stats;
 
 /* Decoded columns of the LAST submit (FA_CFG_COLUMNS).  Device pointers, valid

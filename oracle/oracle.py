@@ -12,6 +12,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB_KIND = None  # "portable" (-march=x86-64-v2, built in the CPU container) or "native" (-march=native, built on this host)
+_MOCKER = None
 
 FO_MAX_KEY_WORDS = 12
 KEY_MODES = {"flows5m": 0, "aspair": 1, "srcaddr": 2, "dstaddr": 3, "5tuple": 4, "srcport": 5, "dstport": 6}
@@ -42,12 +44,57 @@ def build():
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        path = os.path.join(_HERE, "liboracle.so")
+def use_native():
+    """Build oracle/_native/liboracle.so with -march=native ON THIS HOST and use it from now on (bench.py's CPU arms: the
+    baseline gets the box's own ISA).  Falls back to the portable build when there is no compiler.
+    Must be called before the first oracle call of the process.  Returns the kind in use."""
+    global _LIB_KIND
+    if _LIB is not None:
+        return _LIB_KIND
+    r = subprocess.run(["make", "-s", "-C", _HERE, "native"], capture_output=True, text=True)
+    _LIB_KIND = "native" if r.returncode == 0 and os.path.exists(os.path.join(_HERE, "_native", "liboracle.so")) else "portable"
+    return _LIB_KIND
+
+
+def lib_kind():
+    return _LIB_KIND or "portable"
+
+
+class MockerConfig(C.Structure):
+    """include/flowagg.h: fa_mocker_config (the producer's parameters; mocker/mocker.go:57-102)."""
+    _fields_ = [("seed", C.c_uint64), ("t0", C.c_uint64), ("flows_per_second", C.c_uint64), ("n_src_as", C.c_uint32),
+                ("n_dst_as", C.c_uint32), ("addr_mode", C.c_uint32), ("framed", C.c_uint32)]
+
+
+def mocker_host(seed=1, t0=1584912398, flows_per_second=0, n_src_as=3, n_dst_as=3, addr_mode=0, framed=True, first=0, n=0):
+    """The synthetic producer's records [first, first+n) from oracle/libmocker_ref.so (host only; never maps libflowagg.so)."""
+    global _MOCKER
+    if _MOCKER is None:
+        path = os.path.join(_HERE, "libmocker_ref.so")
         if not os.path.exists(path):
             build()
+        _MOCKER = C.CDLL(path)
+        _MOCKER.fo_mocker_host.restype = C.c_int
+        _MOCKER.fo_mocker_host.argtypes = [C.POINTER(MockerConfig), C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                           C.POINTER(C.c_size_t)]
+    cfg = MockerConfig(seed, t0, flows_per_second, n_src_as, n_dst_as, addr_mode, 1 if framed else 0)
+    nbytes = C.c_size_t(0)
+    _MOCKER.fo_mocker_host(C.byref(cfg), first, n, None, 0, None, C.byref(nbytes))
+    buf = np.empty(nbytes.value, dtype=np.uint8)
+    offs = np.empty(n + 1, dtype=np.uint32)
+    rc = _MOCKER.fo_mocker_host(C.byref(cfg), first, n, buf.ctypes.data, buf.size, offs.ctypes.data, C.byref(nbytes))
+    if rc != 0:
+        raise RuntimeError(f"fo_mocker_host failed: {rc}")
+    return buf, offs
+
+
+def lib():
+    global _LIB, _LIB_KIND
+    if _LIB is None:
+        path = os.path.join(_HERE, "_native", "liboracle.so") if _LIB_KIND == "native" else os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB_KIND = _LIB_KIND or "portable"
         L = C.CDLL(path)
         L.fo_decode.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(FoFlow)]
         L.fo_decode.restype = C.c_int

@@ -40,6 +40,18 @@ def edge_cases():
 
 
 @pytest.fixture(scope="session")
+def rollup_boundaries():
+    with open(os.path.join(GOLDEN, "rollup_boundaries.json")) as f:
+        return json.load(f)
+
+
+def rollup_case_rows(case):
+    """Expected flows_5m rows of one tests/golden/rollup_boundaries.json case as (key words, bytes, packets, count) tuples in
+    the table's ORDER BY order (create.sh:88-90); Date is derived from Timeslot and checked separately."""
+    return [((r["Timeslot"], r["SrcAS"], r["DstAS"], r["EType"]), r["Bytes"], r["Packets"], r["Count"]) for r in case["rows"]]
+
+
+@pytest.fixture(scope="session")
 def mocker_10k():
     return dict(np.load(os.path.join(GOLDEN, "mocker_10k.npz")))
 

@@ -609,6 +609,88 @@ def test_schemaless_wire_fuzz_gpu_equals_oracle(fp, oracle, torch_cuda, seed):
             assert np.array_equal(a.flush(), want)
 
 
+def _addr_text(oracle, cols, name, i):
+    """net.IP.String() of the column value (inserter.go:131-140); longer than 16 bytes: "?" + hex of the 16 kept bytes + ".."."""
+    ln = int(cols[name + "_len"][i])
+    if ln > 16:
+        return "?" + bytes(cols[name][i][:16]).hex() + ".."
+    return oracle.ip_string(bytes(cols[name][i][:ln]))
+
+
+def test_host_inserter_copy_sink_and_metrics_scrape(fp, oracle, torch_cuda, fuzz_2k, tmp_path):
+    """-sink copy: the inserter's 14-column row (inserter.go:51-66,142-157) as a Postgres COPY script, checked field by field
+    against the oracle; -metrics: insert_count (inserter.go:44-49) and the bad-record counter scraped from the endpoint
+    (inserter.go:69-73) equal the oracle's counts, and the GPU-busy counter is alive."""
+    import os
+    import socket
+    import subprocess
+    import time
+    import urllib.request
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "flow-pipeline_b200", "host", "flowagg-inserter")
+    g = fuzz_2k
+    msgs = [bytes(g["blob"][g["offsets"][i]:g["offsets"][i + 1]]) for i in range(len(g["offsets"]) - 1)]
+    msgs += [b"\x32\x04" + bytes([192, 168, 1, 1]) + b"\x3a\x10" + bytes(10) + b"\xff\xff" + bytes([10, 0, 0, 7]) + b"\x48\x05" + b"\xb0\x02\x8e\xb0\xdf\xf3\x05",
+             b"\x32\x11" + bytes(range(17)) + b"\x48\x07", b"\xff\xff\xff", b"\x48"]       # a 17-byte address; two undecodable messages
+    blob, offs = concat_records(frame(msgs))
+    f = tmp_path / "claim.bin"
+    f.write_bytes(blob.tobytes())
+    out = tmp_path / "rows.copy"
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    proc = subprocess.Popen([exe, "-claim.file", str(f), "-sink", "copy", "-flush.count", "0", "-out", str(out), "-metrics", "-metrics.addr",
+                             f":{port}", "-linger", "60s"], stderr=subprocess.PIPE, text=True)
+    cols = oracle.decode_columns(blob, offs, framed=True)
+    n_good, n_bad = int(cols["valid"].sum()), int((~cols["valid"].astype(bool)).sum())
+    assert n_bad >= 2
+    scraped = {}
+    try:
+        deadline = time.time() + 50
+        while time.time() < deadline:
+            try:
+                body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=2).read().decode()
+            except OSError:
+                time.sleep(0.2)
+                continue
+            scraped = {l.split()[0]: float(l.split()[1]) for l in body.splitlines() if l and not l.startswith("#")}
+            if scraped.get("flowagg_records_total", 0) == len(msgs):
+                break
+            time.sleep(0.2)
+    finally:
+        proc.terminate()
+        err = proc.communicate(timeout=30)[1]
+    assert scraped.get("flowagg_records_total") == len(msgs), (scraped, err[-500:])
+    assert scraped["insert_count"] == n_good and scraped["flowagg_bad_records_total"] == n_bad
+    assert scraped["flowagg_gpu_busy_seconds_total"] > 0
+    lines = out.read_text().splitlines()
+    assert lines[0].startswith("COPY flows (date_inserted, time_flow, type, sampling_rate, src_ip, dst_ip, bytes, packets, src_port, dst_port, "
+                               "etype, proto, src_as, dst_as) FROM stdin;")
+    body = lines[1:]
+    if body and body[-1] == "\\.":            # the end-of-data marker is written on a clean shutdown
+        body = body[:-1]
+    want = []
+    for i in range(len(msgs)):
+        if not cols["valid"][i]:
+            continue
+        ty = int(cols["type"][i])
+        ty = ty - (1 << 32) if ty >= (1 << 31) else ty
+        tf = time.strftime("%Y-%m-%d %H:%M:%S+00", time.gmtime(int(cols["time_flow_start"][i]) & ((1 << 63) - 1))) if int(cols["time_flow_start"][i]) < (1 << 40) else None
+        want.append((tf, [str(ty), str(int(cols["sampling_rate"][i])), _addr_text(oracle, cols, "src_addr", i), _addr_text(oracle, cols, "dst_addr", i),
+                          str(int(cols["bytes"][i])), str(int(cols["packets"][i])), str(int(cols["src_port"][i])), str(int(cols["dst_port"][i])),
+                          str(int(cols["etype"][i])), str(int(cols["proto"][i])), str(int(cols["src_as"][i])), str(int(cols["dst_as"][i]))]))
+    assert len(body) == len(want) == n_good
+    for line, (tf, rest) in zip(body, want):
+        parts = line.split("\t")
+        assert len(parts) == 14 and parts[2:] == rest
+        assert len(parts[0]) == 22 and parts[0].endswith("+00")          # date_inserted: NOW() at the time of the copy
+        if tf is not None:
+            assert parts[1] == tf
+    assert any("\t192.168.1.1\t10.0.0.7\t" in l for l in body) and any("\t?000102030405060708090a0b0c0d0e0f..\t" in l for l in body)
+
+
 def test_host_inserter_mirror_row_sink_matches_the_inserters_14_columns(fp, oracle, torch_cuda, fuzz_2k, tmp_path):
     """-sink rows: one row per decoded flow, columns and IP formatting of inserter.go:131-157
     (net.IP.String incl. v4, v4-mapped, "?hex" and the "<nil>" -> 0.0.0.0 patch)."""
@@ -636,8 +718,7 @@ def test_host_inserter_mirror_row_sink_matches_the_inserters_14_columns(fp, orac
             continue
         ty = int(cols["type"][i])
         ty = ty - (1 << 32) if ty >= (1 << 31) else ty
-        sip = oracle.ip_string(bytes(cols["src_addr"][i][: min(int(cols["src_addr_len"][i]), 16)]))
-        dip = oracle.ip_string(bytes(cols["dst_addr"][i][: min(int(cols["dst_addr_len"][i]), 16)]))
+        sip, dip = _addr_text(oracle, cols, "src_addr", i), _addr_text(oracle, cols, "dst_addr", i)
         want.append("\t".join(["NOW()", str(int(cols["time_flow_start"][i])), str(ty), str(int(cols["sampling_rate"][i])), sip, dip,
                                str(int(cols["bytes"][i])), str(int(cols["packets"][i])), str(int(cols["src_port"][i])),
                                str(int(cols["dst_port"][i])), str(int(cols["etype"][i])), str(int(cols["proto"][i])),
@@ -786,3 +867,27 @@ def test_readme_sample_rows_on_the_gpu(fp, oracle, torch_cuda):
     assert np.array_equal(rows, want)
     assert [(int(r["key"][0]), int(r["key"][2]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in rows] == \
         [(1584912300, 65000, 2930, 152, 4), (1584912300, 65001, 1935, 190, 3), (1584912300, 65002, 4820, 288, 6)]
+
+
+@pytest.mark.gpu
+def test_rollup_boundary_vectors_on_the_gpu(fp, oracle, torch_cuda, rollup_boundaries):
+    """tests/golden/rollup_boundaries.json through the C ABI: slot edges, day rollover, DateTime wrap, UInt64 wrap of the sums,
+    the all-ones key (the table's reserved side slot) -- rows bytewise equal to the independently computed expectation."""
+    from conftest import rollup_case_rows
+
+    for case in rollup_boundaries["cases"]:
+        msgs = [bytes.fromhex(h) for h in case["messages_hex"]]
+        for framed in (False, True):
+            blob, offs = concat_records(frame(msgs) if framed else msgs)
+            with fp.FlowAgg("flows5m", device=0) as a:
+                a.submit(blob, offs, framed=framed)
+                rows = a.flush()
+                got = [(tuple(int(x) for x in r["key"][:4]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in rows]
+                assert got == rollup_case_rows(case), (case["name"], framed)
+                # the same flows again, twice, into the emptied table: every sum doubles modulo 2^64
+                a.submit(blob, offs, framed=framed)
+                a.submit(blob, offs, framed=framed)
+                rows = a.flush()
+                got = [(tuple(int(x) for x in r["key"][:4]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in rows]
+                want = [(k, (2 * b) & (2 ** 64 - 1), (2 * p) & (2 ** 64 - 1), 2 * c) for k, b, p, c in rollup_case_rows(case)]
+                assert got == want, (case["name"], framed)

@@ -182,9 +182,41 @@ def test_bench_reference_arm_contract_on_cpu():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "flows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("configs[1]") and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
+    # same config tag as the GPU arm (the driver compares the two lines)
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.bench_config() and d["cpu_baseline"]["isa"] in ("native", "portable")
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """The CPU arm's input comes from oracle/libmocker_ref.so: the product library must not be in the process's maps."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','1','--flows','200000'];"
+            "import runpy\n"
+            "try:\n    runpy.run_path(%r, run_name='__main__')\nexcept SystemExit: pass\n"
+            "maps=open('/proc/self/maps').read(); sys.stderr.write('MAPS_HAS_FLOWAGG=%%d\\n' %% ('libflowagg' in maps)); "
+            "sys.stderr.write('MAPS_HAS_ORACLE=%%d\\n' %% ('liboracle' in maps))") % os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "MAPS_HAS_FLOWAGG=0" in r.stderr and "MAPS_HAS_ORACLE=1" in r.stderr, r.stderr[-1500:]
+
+
+def test_oracle_side_mocker_is_bytewise_the_product_mocker(fp, oracle):
+    """oracle/libmocker_ref.so (the CPU arms' producer) and fa_mocker_host emit the same bytes for the same (config, index)."""
+    for kw in (dict(seed=1, flows_per_second=250_000, n_src_as=256, n_dst_as=256, framed=True),
+               dict(seed=9, flows_per_second=0, n_src_as=3, n_dst_as=3, framed=False),
+               dict(seed=4, flows_per_second=7, n_src_as=16, n_dst_as=5, framed=True, addr_mode=1),
+               dict(seed=5, flows_per_second=7, n_src_as=16, n_dst_as=5, framed=True, addr_mode=2)):
+        for first in (0, 2 ** 28 - 50, 2 ** 32 - 100):
+            cfg = fp.FaMockerConfig.make(**kw)
+            a, ao = fp.mocker_host(cfg, first, 3000)
+            b, bo = oracle.mocker_host(first=first, n=3000, **kw)
+            assert np.array_equal(a, b) and np.array_equal(ao, bo)
 
 
 def test_bench_gpu_arm_fails_loudly_without_a_gpu():

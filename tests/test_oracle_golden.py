@@ -167,3 +167,29 @@ def test_rollup_reproduces_the_readme_sample_rows(oracle):
     assert got == [("2020-03-22", "2020-03-22 21:25:00", 65001, 65000, 34525, 2930, 152, 4),
                    ("2020-03-22", "2020-03-22 21:25:00", 65001, 65001, 34525, 1935, 190, 3),
                    ("2020-03-22", "2020-03-22 21:25:00", 65001, 65002, 34525, 4820, 288, 6)]   # README.md:180-183, in its ORDER BY order
+
+
+def _rows_as_tuples(rows):
+    return [(tuple(int(x) for x in r["key"][:4]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in rows]
+
+
+def test_rollup_boundary_vectors(oracle, rollup_boundaries):
+    """The Clickhouse half at its edges (tests/golden/make_rollup_golden.py: expected rows computed there from the documented
+    semantics of toStartOfFiveMinute / toDate / DateTime / UInt64 sum, independently of the oracle): five-minute slot edges,
+    day rollover, the DateTime's 32-bit wrap, UInt64 wrap of the sums, EType never merging, extreme AS numbers, the all-ones key."""
+    from conftest import rollup_case_rows
+
+    for case in rollup_boundaries["cases"]:
+        msgs = [bytes.fromhex(h) for h in case["messages_hex"]]
+        for framed in (False, True):
+            blob, offs = concat_records(frame(msgs) if framed else msgs)
+            rows, _, res = oracle.run_batch(blob, offs, framed=framed, key_mode="flows5m")
+            assert res["n_bad"] == 0 and res["n_records"] == len(msgs), case["name"]
+            assert _rows_as_tuples(rows) == rollup_case_rows(case), case["name"]
+            for r, w in zip(rows, case["rows"]):
+                assert int(r["key"][0]) // 86400 == w["Date"], case["name"]          # toDate(TimeReceived): fa_row_date / create.sh:66
+        # a second pass over the same flows doubles every sum modulo 2^64 (SummingMergeTree merge of two parts, create.sh:88)
+        blob, offs = concat_records(msgs + msgs)
+        rows, _, _ = oracle.run_batch(blob, offs, framed=False, key_mode="flows5m")
+        want = [(k, (2 * b) & (2 ** 64 - 1), (2 * p) & (2 ** 64 - 1), 2 * c) for k, b, p, c in rollup_case_rows(case)]
+        assert _rows_as_tuples(rows) == want, case["name"]
