@@ -106,15 +106,6 @@ struct Flow {
     uint32_t src_len, dst_len, sampler_len;
 };
 
-FA_DEV __forceinline__ void flow_reset(Flow &f)
-{
-    f.time_received = f.sampling_rate = f.time_flow_start = f.bytes = f.packets = 0;
-    f.type = f.sequence_num = f.src_as = f.dst_as = f.etype = f.proto = f.src_port = f.dst_port = 0;
-FA_UNROLL
-    for (int i = 0; i < 4; i++) f.src[i] = f.dst[i] = f.sampler[i] = 0;
-    f.src_len = f.dst_len = f.sampler_len = 0;
-}
-
 #define FA_MAX_GROUP_DEPTH 32
 
 // Byte source over aligned 32-bit words in GLOBAL memory; over-reads are clamped
@@ -506,322 +497,13 @@ FA_DEV __forceinline__ bool decode_record(const Src s, uint32_t pos, uint32_t en
     return decode_message<NEED>(s, pos, end, f);
 }
 
-// ---- the shape fast path -----------------------------------------------------------------------
-//
-// Every protobuf serializer (Go's proto.Marshal at mocker/mocker.go:97 included) writes each field at most once,
-// in ascending field-number order, and proto3 leaves zero values out.  The records of one producer therefore
-// all look like a SUBSEQUENCE of one short list of tags.  The fast path walks that list in lock step -- "does my
-// cursor sit on this tag?  then consume the field" -- with no per-lane dispatch on field number or wire type:
-//
-//   * the fields a kernel KEEPS are known at compile time (its NEED mask): each is a piece of straight-line code
-//     with its tag, wire type and destination register as immediates;
-//   * between two kept fields sits a SEGMENT of the ShapeTable: the other tags the producer sends, learned from a
-//     sample of the batch (shape_collect / shape_build), validated and skipped by one small loop.
-//
-// The fast path ACCEPTS a record only when its bytes are exactly a sequence of such fields in ascending order, each
-// with a 1..5-byte varint, a 1-byte length or a fixed-width value, ending on the record's last byte; the values it
-// kept are then the values proto.Unmarshal keeps (no duplicates, so last-wins is moot).  Anything else -- unknown
-// or repeated tags, another order, long varints, groups, strings -- is NOT decided here: the caller re-parses the
-// record with decode_record (the order-agnostic decoder above).  Results never depend on the table.
-constexpr uint32_t kShapeMax = 48;
-constexpr uint32_t kShapeNoSlot = 31;
-constexpr uint32_t kKeptFields = 16;
-// flags a learned tag value carries above its 14 bits
-constexpr uint16_t kTagSaw4 = 1u << 14;  // a varint of 1..4 bytes was seen for this tag
-constexpr uint16_t kTagSaw5 = 1u << 15;  // a 5-byte varint was seen
-
-// skip-step word: bits 0-15 the tag bytes as they appear in the stream (little endian), then one-hot kind bits.  No
-// kind bit = "varint of 1..4 bytes": the commonest step is the one with no flag set.  The three varint kinds differ
-// in the lengths they take (V5: exactly 5 bytes -- every Unix timestamp since 1978 --, V45: 1..5); which one a tag
-// gets is learned from the lengths seen in the sample.
-constexpr uint32_t kStepV5 = 1u << 24, kStepV45 = 1u << 25, kStepLen = 1u << 26, kStepFixed32 = 1u << 27, kStepFixed64 = 1u << 28;
-constexpr uint32_t kStepNotPlain = 0x1Fu << 24;
-
-struct ShapeTable {
-    // seg[i]: skip steps in front of the i-th kept field of the kernel (i = its rank among the kernel's kept fields in
-    // tag order; the last used entry is the tail behind the last kept field): count with one-byte tags | count with
-    // two-byte tags << 8.  Their words follow each other in step[], one-byte tags first within a segment.
-    uint32_t seg[kKeptFields + 1];
-    uint32_t step[kShapeMax + 1];  // + one spare word (shape_skip reads one step ahead)
-};
-
-// schema of pb-ext/flow.pb.go:58-143 for the fields the kernels keep: F_* bit index -> tag value (num << 3 | wt).
-// Ascending, like the bits themselves.
-FA_DEV constexpr uint32_t shape_tag_of_bit(int bit)
+FA_DEV __forceinline__ void flow_reset(Flow &f)
 {
-    constexpr uint32_t t[kKeptFields] = {(1u << 3) | 0u,  (2u << 3) | 0u,  (3u << 3) | 0u,  (4u << 3) | 0u,  (6u << 3) | 2u,  (7u << 3) | 2u,
-                                        (9u << 3) | 0u,  (10u << 3) | 0u, (11u << 3) | 2u, (14u << 3) | 0u, (15u << 3) | 0u, (20u << 3) | 0u,
-                                        (21u << 3) | 0u, (22u << 3) | 0u, (30u << 3) | 0u, (38u << 3) | 0u};
-    return t[bit];
-}
-FA_DEV __forceinline__ uint32_t shape_slot_of(uint32_t tagval)
-{
-    for (int b = 0; b < (int)kKeptFields; b++)
-        if (shape_tag_of_bit(b) == tagval) return (uint32_t)b;
-    return kShapeNoSlot;
-}
-// tag value -> its bytes in the stream, little endian (one byte below 128, two below 2^14)
-FA_DEV constexpr uint32_t shape_raw_tag(uint32_t tagval) { return tagval >= 128u ? ((tagval & 0x7fu) | 0x80u | ((tagval >> 7) << 8)) : tagval; }
-
-// Can a field with this tag value be a step at all?  Field numbers 1..2047 (1-2 tag bytes), wire types
-// 0/1/2/5, and not the two proto3 strings (100, 101: UTF-8 is checked by the generic decoder only).
-FA_DEV __forceinline__ bool shape_tag_ok(uint32_t tagval)
-{
-    const uint32_t num = tagval >> 3, wt = tagval & 7u;
-    if (num < 1u || num > 2047u) return false;
-    if (wt != 0u && wt != 1u && wt != 2u && wt != 5u) return false;
-    if ((num == 100u || num == 101u) && wt == 2u) return false;
-    return true;
-}
-
-// Learned tag values (bits 14/15 = kTagSaw4/kTagSaw5, neither = lengths unknown) -> table for a kernel that keeps the
-// fields in `need`.  More than kShapeMax tags: no learned steps (the kept fields alone are still walked).
-FA_DEV inline void shape_build(const uint16_t *tags, uint32_t n, uint32_t need, ShapeTable &t)
-{
-    for (uint32_t i = 0; i <= kKeptFields; i++) t.seg[i] = 0;
-    if (n > kShapeMax) n = 0;
-    uint32_t n_steps = 0, segment = 0, lo = 0;  // lo: first tag value of the current segment
-    // segment boundaries: the kept fields' tag values, ascending; the segment after the last one has no upper bound
-    for (int bit = 0; bit <= (int)kKeptFields; bit++) {
-        if (bit < (int)kKeptFields && !((need >> bit) & 1u)) continue;
-        const uint32_t hi = bit < (int)kKeptFields ? shape_tag_of_bit(bit) : 0x10000u;
-        for (int two = 0; two < 2; two++)  // one-byte tags first (ascending order has them first anyway)
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t tagval = tags[i] & 0x3fffu, wt = tagval & 7u;
-                if (!shape_tag_ok(tagval) || (tagval >= 128u) != (two != 0)) continue;
-                if (tagval < lo || tagval >= hi) continue;
-                const uint32_t slot = shape_slot_of(tagval);
-                if (slot != kShapeNoSlot && ((need >> slot) & 1u)) continue;  // a kept field: compiled code, not a step
-                const bool saw4 = (tags[i] & kTagSaw4) != 0, saw5 = (tags[i] & kTagSaw5) != 0;
-                const uint32_t kind = wt == 0u ? (saw4 == saw5 ? kStepV45 : (saw5 ? kStepV5 : 0u))
-                                               : (wt == 2u ? kStepLen : (wt == 5u ? kStepFixed32 : kStepFixed64));
-                t.step[n_steps++] = shape_raw_tag(tagval) | kind;
-                t.seg[segment] += two ? 1u << 8 : 1u;
-            }
-        segment++;
-        lo = hi + 1u;  // the next segment starts behind this kept field's tag value
-    }
-    t.step[n_steps] = 0u;  // the look-ahead word
-}
-
-// Walk one sampled record and report every field a step could stand for: calls seen(tagval, value_bytes) per field
-// (value_bytes: the varint's length, 0 for the other wire types).  Stops at the first thing the fast path would not
-// take (the record then teaches what it showed so far).
-template <class Src, class Seen>
-FA_DEV __forceinline__ void shape_collect(const Src s, uint32_t pos, const uint32_t end, bool framed, Seen seen)
-{
-    if (framed) {  // skip the length prefix (1-2 bytes; longer ones are not worth learning from)
-        if (pos >= end) return;
-        const uint32_t b0 = s.byte(pos);
-        pos += (b0 & 0x80u) ? 2u : 1u;
-    }
-    for (uint32_t guard = 0; guard < 2u * kShapeMax && pos < end; guard++) {
-        const uint32_t b0 = s.byte(pos);
-        uint32_t tagval = b0 & 0x7fu, tl = 1u;
-        if (b0 & 0x80u) {
-            if (pos + 1u >= end) return;
-            const uint32_t b1 = s.byte(pos + 1u);
-            if ((b1 & 0x80u) || b1 == 0u) return;  // 3+ bytes, or an over-long encoding
-            tagval |= b1 << 7;
-            tl = 2u;
-        }
-        if (!shape_tag_ok(tagval)) return;
-        pos += tl;
-        const uint32_t wt = tagval & 7u;
-        uint32_t vb = 0;
-        if (wt == 0u) {
-            uint32_t k = 0;
-            while (k < 5u && pos + k < end && (s.byte(pos + k) & 0x80u)) k++;
-            if (k >= 5u || pos + k >= end) return;
-            vb = k + 1u;
-            pos += vb;
-        } else if (wt == 2u) {
-            if (pos >= end) return;
-            const uint32_t ln = s.byte(pos);
-            if (ln & 0x80u) return;
-            pos += 1u + ln;
-        } else {
-            pos += wt == 5u ? 4u : 8u;
-        }
-        if (pos > end) return;
-        seen(tagval, vb);
-    }
-}
-
-// 4 x 7 payload bits of the varint bytes in x -> 28-bit value
-FA_DEV __forceinline__ uint32_t shape_low28(uint32_t x)
-{
-    return (x & 0x7fu) | ((x >> 1) & 0x3f80u) | ((x >> 2) & 0x1fc000u) | ((x >> 3) & 0xfe00000u);
-}
-
-// NR records' share of `count` skip steps starting at byte offset jo of sh.step, tags TWO ? two bytes : one byte long.
-// The table walk (step word, loop, dispatch on the step's kind) is paid once per step for all NR records.
-template <bool TWO, int NR, class Src>
-FA_DEV __forceinline__ void shape_skip(const ShapeTable &sh, const Src s, uint32_t &jo, const uint32_t count, uint32_t (&pos)[NR],
-                                       const uint32_t (&end)[NR])
-{
-    constexpr uint32_t TMASK = TWO ? 0xffffu : 0xffu, TSH = TWO ? 16u : 8u, TL = TWO ? 2u : 1u;
-    const uint32_t je = jo + count * 4u;
-    // the next step's word is fetched one step ahead (an indexed constant load sits on the loop's critical path otherwise);
-    // step[] has a spare word behind the last step, so the look-ahead never leaves the table
-    uint32_t st_next = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sh.step) + jo);
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#endif
-    for (; jo != je; jo += 4u) {
-        const uint32_t st = st_next;
-        st_next = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(sh.step) + jo + 4u);
-        uint32_t x[NR], hi[NR];
-        bool m[NR];
+    f.time_received = f.sampling_rate = f.time_flow_start = f.bytes = f.packets = 0;
+    f.type = f.sequence_num = f.src_as = f.dst_as = f.etype = f.proto = f.src_port = f.dst_port = 0;
 FA_UNROLL
-        for (int q = 0; q < NR; q++) {
-            uint32_t lo;
-            s.window(pos[q], lo, hi[q]);
-            m[q] = (((lo ^ st) & TMASK) == 0u) && pos[q] < end[q];
-            x[q] = funnel_r(lo, hi[q], TSH);  // value bytes 0-3
-        }
-        if (!(st & kStepNotPlain)) {
-            // a varint of 1..4 bytes: the commonest step
-FA_UNROLL
-            for (int q = 0; q < NR; q++) {
-                const uint32_t t = find_first_set(~x[q] & 0x80808080u);  // 8, 16, 24, 32; 0: no terminator in four bytes
-                pos[q] += (m[q] && t != 0u) ? TL + (t >> 3) : 0u;
-            }
-        } else if (st & kStepV5) {
-FA_UNROLL
-            for (int q = 0; q < NR; q++) {
-                const bool five = (x[q] & 0x80808080u) == 0x80808080u && !((hi[q] >> TSH) & 0x80u);
-                pos[q] += (m[q] && five) ? TL + 5u : 0u;
-            }
-        } else if (st & kStepLen) {
-FA_UNROLL
-            for (int q = 0; q < NR; q++) pos[q] += (m[q] && !(x[q] & 0x80u)) ? TL + 1u + (x[q] & 0x7fu) : 0u;  // one-byte lengths only
-        } else if (st & kStepV45) {
-FA_UNROLL
-            for (int q = 0; q < NR; q++) {
-                const uint32_t stop = ~x[q] & 0x80808080u;
-                uint32_t t = find_first_set(stop);
-                t = (stop == 0u && !((hi[q] >> TSH) & 0x80u)) ? 40u : t;
-                pos[q] += (m[q] && t != 0u) ? TL + (t >> 3) : 0u;
-            }
-        } else {
-FA_UNROLL
-            for (int q = 0; q < NR; q++) pos[q] += m[q] ? TL + ((st & kStepFixed32) ? 4u : 8u) : 0u;
-        }
-    }
-}
-
-// The kept field BIT (an F_* bit index) of NR records: tag, wire type and destination are immediates.
-template <int BIT, int NR, class Src>
-FA_DEV __forceinline__ void shape_keep(const Src s, uint32_t (&pos)[NR], const uint32_t (&end)[NR], Flow (&f)[NR])
-{
-    constexpr uint32_t TAG = shape_tag_of_bit(BIT), RAW = shape_raw_tag(TAG);
-    constexpr bool TWO = TAG >= 128u;
-    constexpr uint32_t TMASK = TWO ? 0xffffu : 0xffu, TSH = TWO ? 16u : 8u, TL = TWO ? 2u : 1u;
-FA_UNROLL
-    for (int q = 0; q < NR; q++) {
-        uint32_t lo, hi;
-        s.window(pos[q], lo, hi);
-        bool m = ((lo & TMASK) == RAW) && pos[q] < end[q];
-        const uint32_t x = funnel_r(lo, hi, TSH), y = hi >> TSH;  // value bytes 0-3, 4..
-        if ((TAG & 7u) == 2u) {
-            // bytes: SrcAddr / DstAddr / SamplerAddress
-            const uint32_t ln = x & 0x7fu;
-            m = m && !(x & 0x80u);  // two-byte lengths: not decided here
-            uint32_t a[4];
-            load_addr(s, pos[q] + TL + 1u, ln, a);
-            uint32_t *dst = BIT == 4 ? f[q].src : (BIT == 5 ? f[q].dst : f[q].sampler);
-            uint32_t &dlen = BIT == 4 ? f[q].src_len : (BIT == 5 ? f[q].dst_len : f[q].sampler_len);
-FA_UNROLL
-            for (int k = 0; k < 4; k++) dst[k] = m ? a[k] : dst[k];
-            dlen = m ? ln : dlen;
-            pos[q] += m ? TL + 1u + ln : 0u;
-        } else {
-            const uint32_t stop = ~x & 0x80808080u;  // terminators among the first four bytes
-            uint32_t t = find_first_set(stop);       // 8, 16, 24, 32; 0: none
-            t = (stop == 0u && !(y & 0x80u)) ? 40u : t;
-            m = m && t != 0u;  // six bytes or more: not decided here
-            const uint32_t keep_bits = t >= 32u ? 0xFFFFFFFFu : (0xFFFFFFFFu >> ((32u - t) & 31u));
-            const uint32_t b4 = t == 40u ? (y & 0x7fu) : 0u;  // bits 28..34
-            const uint32_t vlo = shape_low28(x & keep_bits) | (b4 << 28), vhi = b4 >> 4;
-            const unsigned long long v = ((unsigned long long)vhi << 32) | vlo;
-            // consumeUint64 / consumeUint32 / consumeEnum: u32 = low 32 bits
-            if (BIT == 0) f[q].type = m ? vlo : f[q].type;
-            if (BIT == 1) f[q].time_received = m ? v : f[q].time_received;
-            if (BIT == 2) f[q].sampling_rate = m ? v : f[q].sampling_rate;
-            if (BIT == 3) f[q].sequence_num = m ? vlo : f[q].sequence_num;
-            if (BIT == 6) f[q].bytes = m ? v : f[q].bytes;
-            if (BIT == 7) f[q].packets = m ? v : f[q].packets;
-            if (BIT == 9) f[q].src_as = m ? vlo : f[q].src_as;
-            if (BIT == 10) f[q].dst_as = m ? vlo : f[q].dst_as;
-            if (BIT == 11) f[q].proto = m ? vlo : f[q].proto;
-            if (BIT == 12) f[q].src_port = m ? vlo : f[q].src_port;
-            if (BIT == 13) f[q].dst_port = m ? vlo : f[q].dst_port;
-            if (BIT == 14) f[q].etype = m ? vlo : f[q].etype;
-            if (BIT == 15) f[q].time_flow_start = m ? v : f[q].time_flow_start;
-            pos[q] += m ? TL + (t >> 3) : 0u;
-        }
-    }
-}
-
-// segment SEG of the table (both tag lengths), then -- for BIT < 16 -- the kept field BIT, then on to the next bit
-template <uint32_t NEED, int BIT, int SEG, int NR, class Src>
-struct ShapeWalk {
-    static FA_DEV __forceinline__ void run(const ShapeTable &sh, const Src s, uint32_t &jo, uint32_t (&pos)[NR], const uint32_t (&end)[NR],
-                                           Flow (&f)[NR])
-    {
-        constexpr bool KEPT = BIT < (int)kKeptFields && ((NEED >> (BIT < (int)kKeptFields ? BIT : 0)) & 1u);
-        if (KEPT || BIT == (int)kKeptFields) {
-            const uint32_t sg = sh.seg[SEG];
-            shape_skip<false, NR>(sh, s, jo, sg & 0xffu, pos, end);
-            shape_skip<true, NR>(sh, s, jo, (sg >> 8) & 0xffu, pos, end);
-        }
-        if (KEPT) shape_keep<(BIT < (int)kKeptFields ? BIT : 0), NR>(s, pos, end, f);
-        ShapeWalk<NEED, BIT + 1, SEG + (KEPT ? 1 : 0), NR, Src>::run(sh, s, jo, pos, end, f);
-    }
-};
-template <uint32_t NEED, int SEG, int NR, class Src>
-struct ShapeWalk<NEED, (int)kKeptFields + 1, SEG, NR, Src> {
-    static FA_DEV __forceinline__ void run(const ShapeTable &, const Src, uint32_t &, uint32_t (&)[NR], const uint32_t (&)[NR], Flow (&)[NR]) {}
-};
-
-// Framed or bare records [pos,end) through the shape fast path, NR at a time.  taken[q] true: f[q] holds record q's
-// fields.  false: undecided -- the caller resets f[q] and runs decode_record (the order-agnostic decoder).  Records
-// with pos == end are idle lanes' placeholders: never taken.  f must be zero-initialised.
-template <uint32_t NEED, int NR, class Src>
-FA_DEV __forceinline__ void decode_records_shape(const ShapeTable &sh, const Src s, uint32_t (&pos)[NR], const uint32_t (&end)[NR], bool framed,
-                                                 Flow (&f)[NR], bool (&taken)[NR])
-{
-FA_UNROLL
-    for (int q = 0; q < NR; q++) {
-        taken[q] = pos[q] < end[q];  // empty spans are the order-agnostic decoder's business
-        if (framed) {  // varint(len) || message, len must fill the span: mocker/mocker.go:98-101
-            uint32_t lo, hi;
-            s.window(pos[q], lo, hi);
-            const bool one = !(lo & 0x80u);
-            const uint32_t mlen = one ? (lo & 0x7fu) : ((lo & 0x7fu) | ((lo >> 1) & 0x3f80u));
-            const uint32_t hn = one ? 1u : 2u;
-            taken[q] = taken[q] && (one || !(lo & 0x8000u)) && pos[q] + hn <= end[q] && mlen == end[q] - pos[q] - hn;
-            pos[q] = taken[q] ? pos[q] + hn : end[q];
-        }
-    }
-    uint32_t jo = 0;
-    ShapeWalk<NEED, 0, 0, NR, Src>::run(sh, s, jo, pos, end, f);
-FA_UNROLL
-    for (int q = 0; q < NR; q++) taken[q] = taken[q] && pos[q] == end[q];
-}
-
-// one record (the CPU harness and single-record callers)
-template <uint32_t NEED, class Src>
-FA_DEV __forceinline__ bool decode_record_shape(const ShapeTable &sh, const Src s, uint32_t pos, uint32_t end, bool framed, Flow &f)
-{
-    uint32_t p[1] = {pos};
-    const uint32_t e[1] = {end};
-    Flow g[1] = {f};
-    bool taken[1];
-    decode_records_shape<NEED, 1>(sh, s, p, e, framed, g, taken);
-    f = g[0];
-    return taken[0];
+    for (int i = 0; i < 4; i++) f.src[i] = f.dst[i] = f.sampler[i] = 0;
+    f.src_len = f.dst_len = f.sampler_len = 0;
 }
 
 }  // namespace fa

@@ -78,15 +78,6 @@ struct fa_ctx {
 
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 
-    // the batch's field list for the decoder's lock-step fast path (decode.cuh): learned on the first submit and
-    // again whenever a flush/stats read shows the order-agnostic decoder took more than 1/8 of the records
-    uint16_t shape_tags[kShapeMax] = {0};
-    uint32_t shape_n = 0;
-    bool shape_known = false, shape_pinned = false, shape_relearn = false, shape_pending = false;
-    ShapeLearned *h_shape = nullptr;  // pinned landing area of k_learn_shape
-    cudaEvent_t ev_shape = nullptr;
-    uint64_t slow_seen = 0, records_seen = 0;  // counters at the last look
-
     // device time of the decode/aggregate kernels: an event pair around every launch, read back lazily
     static constexpr int kBusyRing = 32;
     cudaEvent_t ev_busy[kBusyRing][2] = {};
@@ -233,8 +224,6 @@ extern "C" void fa_destroy(fa_ctx *c)
     cudaFree(c->cols_block);
     cudaFree(c->d_scratch);
     cudaFreeHost(c->h_bounce);
-    cudaFreeHost(c->h_shape);
-    if (c->ev_shape) cudaEventDestroy(c->ev_shape);
     for (auto &pair : c->ev_busy)
         for (cudaEvent_t e : pair)
             if (e) cudaEventDestroy(e);
@@ -336,8 +325,6 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     // it had to be; not combining hot keys would be several times slower)
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
-    FA_CUDA(c, cudaHostAlloc(&c->h_shape, sizeof(ShapeLearned), cudaHostAllocDefault));
-    FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_shape, cudaEventDisableTiming));
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
         FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
         if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * kHotSlots * c->slot_bytes));
@@ -361,30 +348,33 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
 // kernel launch
 // ---------------------------------------------------------------------------------------------
 
-template <class Consumer>
-static cudaError_t launch_tile(fa_ctx *c, TileParams &tp, uint32_t n_tiles)
+template <class Consumer, int THREADS>
+static cudaError_t launch_tile_t(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
-    const size_t smem = 2 * ((size_t)tp.p.tile_bytes + kTilePad + kStreamOffBytes) + kStreamCtlBytes;  // two tile buffers, two offsets slices, barriers/counters/bounds
+    const size_t smem = (size_t)tp.p.tile_bytes + kTilePad + 16;  // tile buffer + over-read pad + mbarrier
     static thread_local unsigned long long configured = 0;  // bit d: done for device d (per kernel instantiation, per thread)
     const unsigned long long dev_bit = 1ull << (c->cfg.device & 63);
-    if (!(configured & dev_bit)) {  // the attribute is per device
-        cudaError_t e = cudaFuncSetAttribute(k_stream<Consumer>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(2 * (kTileBytesMax + kTilePad + kStreamOffBytes) + kStreamCtlBytes));
+    if (smem > 48 * 1024 && !(configured & dev_bit)) {  // the attribute is per device
+        cudaError_t e = cudaFuncSetAttribute(k_tile<Consumer, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileBytesMax + kTilePad + 16));
         if (e != cudaSuccess) return e;
         configured |= dev_bit;
     }
-    // the batch's field list, narrowed to what this consumer keeps (decode.cuh: the lock-step fast path)
-    shape_build(c->shape_tags, c->shape_n, Consumer::NEED, tp.shape);
-    tp.p.n_tiles = n_tiles;
-    tp.p.offsets_aligned = ((uintptr_t)tp.p.offsets & 15u) == 0 ? 1u : 0u;
-    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)(c->num_sms * kStreamBlocksPerSM));  // persistent CTAs
-    k_stream<Consumer><<<grid, kThreads, smem, c->stream>>>(tp);
+    k_tile<Consumer, THREADS><<<n_tiles, THREADS, smem, c->stream>>>(tp);
     c->n_kernels++;
     return cudaGetLastError();
 }
 
+template <class Consumer>
+static cudaError_t launch_tile(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
+{
+    if (tp.p.tile_records <= 128) return launch_tile_t<Consumer, 128>(c, tp, n_tiles);
+    if (tp.p.tile_records <= 256) return launch_tile_t<Consumer, 256>(c, tp, n_tiles);
+    if (tp.p.tile_records <= 512) return launch_tile_t<Consumer, 512>(c, tp, n_tiles);
+    return launch_tile_t<Consumer, 1024>(c, tp, n_tiles);
+}
+
 template <int MODE>
-static cudaError_t launch_fused_mode(fa_ctx *c, TileParams &tp, uint32_t n_tiles)
+static cudaError_t launch_fused_mode(fa_ctx *c, const TileParams &tp, uint32_t n_tiles)
 {
     return c->weighted ? launch_tile<AggConsumer<MODE, true>>(c, tp, n_tiles) : launch_tile<AggConsumer<MODE, false>>(c, tp, n_tiles);
 }
@@ -428,40 +418,6 @@ static uint32_t pick_lane_stride(double avg)
     return best_d;
 }
 
-// The batch's field list (decode.cuh: shape fast path).  First submit of a context: learn from this batch and wait
-// for the answer (once, ~20 us).  Later: re-learn asynchronously when asked to (shape_relearn, set where the
-// counters are read) and adopt the result when its event has fired.  p: buf/offsets/n_records/framed/base/len.
-static int shape_update(fa_ctx *c, const SubmitParams &p)
-{
-    if (c->shape_pinned) return FA_OK;
-    static const bool off = getenv("FA_SHAPE") && atoi(getenv("FA_SHAPE")) == 0;
-    if (off) {
-        c->shape_n = 0;
-        return FA_OK;
-    }
-    auto adopt = [&] {
-        c->shape_n = std::min<uint32_t>(c->h_shape->n, kShapeMax);
-        memcpy(c->shape_tags, c->h_shape->tagval, sizeof c->shape_tags);
-        c->shape_known = true;
-        c->shape_pending = false;
-    };
-    if (c->shape_pending && cudaEventQuery(c->ev_shape) == cudaSuccess) adopt();
-    cudaGetLastError();  // cudaErrorNotReady is not an error
-    if ((!c->shape_known || c->shape_relearn) && !c->shape_pending) {
-        k_learn_shape<<<1, 256, 0, c->stream>>>(p, c->h_shape);
-        c->n_kernels++;
-        FA_CUDA(c, cudaGetLastError());
-        FA_CUDA(c, cudaEventRecord(c->ev_shape, c->stream));
-        c->shape_pending = true;
-        c->shape_relearn = false;
-        if (!c->shape_known) {
-            FA_CUDA(c, cudaEventSynchronize(c->ev_shape));
-            adopt();
-        }
-    }
-    return FA_OK;
-}
-
 // Add the device time of launches whose event pairs have completed (all of them when wait is set).
 static void busy_collect(fa_ctx *c, bool wait)
 {
@@ -497,22 +453,20 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.hint_set = (uint32_t)(c->n_submits & 1u);
     if (c->d_hot) c->hot_dirty = true;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[p.hint_set][0], 0, 8, c->stream));  // this submit's statistics start at zero
-    // tile shape from the batch's mean record size: 256 records per tile when their bytes fit
-    // the shared-memory budget (two buffers per CTA), fewer for fat records
+    // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
+    // the shared-memory budget, fewer for fat records
     const double avg = (double)len / (double)n_records;
-    static const uint32_t max_tile = getenv("FA_TILE_RECORDS") ? (uint32_t)atoi(getenv("FA_TILE_RECORDS")) : (uint32_t)kTileRecords;
-    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~31u, 32u), (uint32_t)kTileRecords);
+    static const uint32_t max_tile = getenv("FA_TILE_RECORDS") ? (uint32_t)atoi(getenv("FA_TILE_RECORDS")) : (uint32_t)kThreads;
+    uint32_t tr = std::min<uint32_t>(std::max<uint32_t>(max_tile & ~31u, 32u), 1024u);
     while (tr > 32 && (double)tr * avg * 1.06 + 512.0 > (double)kTileBytesMax) tr -= 32;
-    uint32_t tb = (uint32_t)std::min<double>((double)tr * avg * 1.06 + 512.0, (double)kTileBytesMax);
-    tb = (tb + 511u) & ~511u;
+    uint32_t tb = (uint32_t)((double)tr * avg * 1.06 + 512.0);
+    tb = (tb + 1023u) & ~1023u;
     if (tb > (uint32_t)kTileBytesMax) tb = kTileBytesMax;
     if (tb < 4096u) tb = 4096u;
     p.tile_records = tr;
     p.tile_bytes = tb;
-    const uint32_t d = tr == (uint32_t)kTileRecords ? pick_lane_stride(avg) : 1u;
+    const uint32_t d = pick_lane_stride(avg);
     p.lane_shift = d == 8 ? 3u : (d == 4 ? 2u : (d == 2 ? 1u : 0u));
-    int rc_shape = shape_update(c, p);
-    if (rc_shape) return rc_shape;
     tp.c = c->cols;
     const uint32_t n_tiles = (n_records + tr - 1) / tr;
     cudaError_t e = cudaSuccess;
@@ -682,21 +636,6 @@ extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32
     return FA_OK;
 }
 
-extern "C" int fa_set_shape(fa_ctx *c, const uint16_t *tag_values, uint32_t n)
-{
-    if (!c || n > kShapeMax || (n && !tag_values)) return FA_ERR_INVALID;
-    if (!tag_values) {  // back to learning from the data
-        c->shape_pinned = false;
-        c->shape_known = false;
-        c->shape_n = 0;
-        return FA_OK;
-    }
-    for (uint32_t i = 0; i < n; i++) c->shape_tags[i] = tag_values[i];
-    c->shape_n = n;
-    c->shape_pinned = true;
-    return FA_OK;
-}
-
 extern "C" int fa_sync(fa_ctx *c)
 {
     if (!c) return FA_ERR_INVALID;
@@ -706,20 +645,10 @@ extern "C" int fa_sync(fa_ctx *c)
     return FA_OK;
 }
 
-// the host just read the counters: did the shape fast path miss too often since the last look?
-static void shape_feedback(fa_ctx *c)
-{
-    const uint64_t slow = c->h_counters->n_slow, recs = c->n_records;
-    if (slow >= c->slow_seen && recs > c->records_seen && (slow - c->slow_seen) * 8 > recs - c->records_seen) c->shape_relearn = true;
-    c->slow_seen = slow;
-    c->records_seen = recs;
-}
-
 static int read_counters(fa_ctx *c)
 {
     FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));
-    shape_feedback(c);
     return FA_OK;
 }
 
@@ -740,7 +669,6 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
     out->n_submits = c->n_submits;
     out->bytes_in = c->bytes_in;
     out->n_kernels = c->n_kernels;
-    out->n_slow = c->h_counters->n_slow;
     busy_collect(c, true);
     out->gpu_busy_us = (uint64_t)c->busy_us;
     return FA_OK;
@@ -917,7 +845,6 @@ static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uin
     FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaMemcpyAsync(dst, rows_out, bytes, cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));  // the one wait
-    shape_feedback(c);
     const uint64_t groups = c->h_counters->n_groups, dropped = c->h_counters->n_dropped;
     if (groups > m) {  // the roll-up grew by more than 1/8: every row is still in scratch, the exact path takes over
         c->last_groups = groups;
@@ -1209,7 +1136,6 @@ extern "C" int fa_reset(fa_ctx *c)
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     c->n_records = c->n_submits = c->bytes_in = 0;
     c->n_kernels = 0;
-    c->slow_seen = c->records_seen = 0;
     busy_collect(c, true);
     c->busy_us = 0;
     return fa_sync(c);

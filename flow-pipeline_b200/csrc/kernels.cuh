@@ -1,21 +1,19 @@
 // kernels.cuh -- sm_100a kernels of the flow-aggregation stage.
 //
-//   k_stream<AggConsumer<MODE,W>>  fused kernel 1 -> kernel 2: length-delimited
-//                                  FlowMessage bytes -> group table (+ sketch).  The
-//                                  columnar intermediate never touches HBM.
-//   k_stream<ColConsumer>          kernel 1 alone: bytes -> 20 decoded columns in HBM
-//                                  (inserter.go:142-157 row + create.sh:36-59 columns).
-//   k_learn_shape                  the batch's field list for the decoder's lock-step fast path (decode.cuh).
-//   k_aggregate_columns<MODE>      kernel 2 alone: columns -> group table (+ sketch).
+//   k_tile<AggConsumer<MODE,W>>  fused kernel 1 -> kernel 2: length-delimited
+//                                FlowMessage bytes -> group table (+ sketch).  The
+//                                columnar intermediate never touches HBM.
+//   k_tile<ColConsumer>          kernel 1 alone: bytes -> 20 decoded columns in HBM
+//                                (inserter.go:142-157 row + create.sh:36-59 columns).
+//   k_aggregate_columns<MODE>    kernel 2 alone: columns -> group table (+ sketch).
 //   k_table_init / k_merge_hot / k_compact_rows / k_estimate   table reset, hot-replica fold, flush, top-K candidates.
 //
-// Stream kernel: persistent CTAs (4 per SM, 256 threads), each walking tiles of <= 256 records.  A tile's byte
-// span AND its slice of the offsets array are brought into one of the CTA's TWO shared-memory buffers by bulk-async
-// copies (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) signalled on an mbarrier, with an L2 evict-first policy so
-// the stream does not push the group table out of L2.  While the 8 warps parse tile k out of one buffer (one thread
-// = one record), the copy of tile k+1 lands in the other; the warp that finishes reading a buffer LAST re-arms it
-// with tile k+2 (its byte bounds were fetched by warp 0 a whole parse earlier and handed over through shared
-// memory), so no warp ever waits at a block-wide barrier and no global load sits between two tiles.
+// Tile kernel: one CTA = one tile of <= 256 records.  The tile's byte span is
+// brought into shared memory by ONE bulk-async copy (cp.async.bulk, the 1-D TMA
+// path: SASS UBLKCP) signalled on an mbarrier, with an L2 evict-first policy so the
+// stream does not push the group table out of L2; then one thread parses one
+// record from shared memory.  Up to 8 CTAs are resident per SM, so copies of some
+// tiles overlap the parsing of others without any intra-CTA pipeline.
 //
 // The path is integer / memory bound: no tensor cores anywhere.
 #pragma once
@@ -28,12 +26,8 @@
 namespace fa {
 
 constexpr int kThreads = 256;            // one record per thread per tile
-constexpr int kTileRecords = kThreads;
-constexpr int kTilePad = 64;             // over-read slack behind each tile buffer
-constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile buffer, upper bound (mocker tile of 256: 21.6 KB -> 23 KB)
-constexpr int kStreamBlocksPerSM = 4;    // 2 x 23 KB buffers per CTA: 4 CTAs = 32 warps per SM, 64 registers per thread
-constexpr int kStreamOffBytes = (kThreads + 8) * 4;  // a tile's slice of the offsets array (n+1 words), per buffer
-constexpr int kStreamCtlBytes = 64;      // mbarriers, reader counters, tile bounds behind the buffers
+constexpr int kTilePad = 64;             // over-read slack behind the tile (then the mbarrier)
+constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile, upper bound (mocker tile of 256: 21.6 KB -> 24 KB)
 
 constexpr uint32_t kHotReplicas = 64;  // CTA b uses replica b mod 64
 constexpr uint32_t kHotSlots = 1024;   // slots per replica (power of two)
@@ -41,7 +35,6 @@ constexpr uint32_t kHotProbes = 8;     // bounded probe sequence; a miss falls t
 
 struct Counters {
     unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows;
-    unsigned long long n_slow;  // records the shape fast path did not decide (parsed by the order-agnostic decoder)
     unsigned int side_state, pad0;
     // key-repetition statistics of the two most recent submits: {lanes whose key repeats inside their warp,
     // lanes looked at}, sampled from every 64th tile.  Submit i decides from what submit i-1 saw.
@@ -56,10 +49,8 @@ struct SubmitParams {
     uint32_t n_records;
     uint32_t framed;
     uint32_t lane_shift;    // log2 of the records between neighbouring lanes of a warp (host-chosen, see pick_lane_stride)
-    uint32_t tile_records;    // records per tile (multiple of 32, <= kTileRecords)
-    uint32_t tile_bytes;      // shared-memory bytes per tile buffer (multiple of 16)
-    uint32_t n_tiles;
-    uint32_t offsets_aligned;  // offsets is 16-byte aligned: a tile's slice of it can be staged by a bulk copy
+    uint32_t tile_records;    // records per CTA tile (<= blockDim.x)
+    uint32_t tile_bytes;      // shared-memory bytes for the tile (multiple of 16); barrier sits behind it
     // group table
     uint8_t *slots;
     uint32_t slot_mask;
@@ -368,32 +359,11 @@ __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long lon
     }
 }
 
-// ---- one decoded flow into the group table (+ sketch), in two halves -----------------------------------
-//
-// begin: key, hash, sketch update, and the LOAD of the first slot of the probe sequence (hot replica or main table);
-// finish: compare, then the three reductions -- or, when the first slot is empty or holds another key, the ordinary
-// probe loop from the start (CAS claim included).  The stream kernel runs `finish` one tile after `begin`, so the
-// L2 round trip of the probe hides behind the parsing of the next record.
-template <int KW>
-struct Probe {
-    static constexpr int KEY64 = KW <= 2 ? 1 : 2;
-    uint8_t *slot;                   // first slot of the probe sequence; nullptr = nothing in flight
-    unsigned long long k[KEY64];     // the flow's key
-    unsigned long long c[KEY64];     // what the slot held
-    unsigned long long h, b, pk;
-    bool hot;
-};
-
-template <int KW>
-__device__ __forceinline__ uint8_t *hot_replica(const SubmitParams &p)
-{
-    return p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES;
-}
-
+// One decoded flow into the group table (+ sketch).  hot: this submit sends updates through the CTA's
+// replica first (keys repeat a lot: one shared slot per key would serialise in L2).
 // Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
 template <int MODE>
-__device__ __forceinline__ uint32_t aggregate_begin(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have,
-                                                    Probe<(KeyTraits<MODE>::KW <= 4 ? KeyTraits<MODE>::KW : 1)> &pr)
+__device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have)
 {
     constexpr int KW = KeyTraits<MODE>::KW;
     uint32_t key[KW];
@@ -408,58 +378,14 @@ __device__ __forceinline__ uint32_t aggregate_begin(const SubmitParams &p, const
         b *= f.sampling_rate;
         pk *= f.sampling_rate;
     }
-    if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
     if (p.slots) {
-        if (KW > 4) {
-            table_add<KW>(p, key, h, b, pk, 1ull);  // wide keys: probed in place (state-word protocol)
-        } else {
-            constexpr int K4 = KW <= 4 ? KW : 1;
-            constexpr int HI = Probe<K4>::KEY64 - 1;
-            pr.k[0] = (unsigned long long)key[0] | (K4 >= 2 ? (unsigned long long)key[K4 >= 2 ? 1 : 0] << 32 : 0ull);
-            if (K4 == 4) pr.k[HI] = (unsigned long long)key[K4 == 4 ? 2 : 0] | ((unsigned long long)key[K4 == 4 ? 3 : 0] << 32);
-            const bool all_ones = K4 == 4 ? (pr.k[0] & pr.k[HI]) == ~0ull : pr.k[0] == ~0ull;
-            if (all_ones) {
-                side_slot_add<K4>(p, b, pk, 1ull);
-            } else {
-                uint8_t *s = hot ? hot_replica<K4>(p) + (size_t)((uint32_t)(h >> 20) & (kHotSlots - 1u)) * SlotLayout<K4>::BYTES
-                                 : p.slots + (size_t)((uint32_t)(h >> 32) & p.slot_mask) * SlotLayout<K4>::BYTES;
-                if (K4 == 4) ld_relaxed_u128(s, pr.c[0], pr.c[HI]);
-                else pr.c[0] = ld_relaxed_u64(s);
-                pr.slot = s;
-                pr.h = h;
-                pr.b = b;
-                pr.pk = pk;
-                pr.hot = hot;
-            }
-        }
-    }
-    return (uint32_t)h;
-}
-
-// The slot holds the key: the three reductions.  Empty, or another key: the ordinary probe loop from the start (CAS
-// claim included).
-template <int KW>
-__device__ __forceinline__ void aggregate_finish(const SubmitParams &p, Probe<KW> &pr)
-{
-    if (!pr.slot) return;
-    constexpr int HI = Probe<KW>::KEY64 - 1;
-    bool same = pr.c[0] == pr.k[0];
-    if (KW == 4) same = same && pr.c[HI] == pr.k[HI];
-    if (same) {
-        slot_add(pr.slot + SlotLayout<KW>::VAL_OFF, pr.b, pr.pk, 1ull);
-    } else {
-        uint32_t key[KW];
-        key[0] = (uint32_t)pr.k[0];
-        if (KW >= 2) key[KW >= 2 ? 1 : 0] = (uint32_t)(pr.k[0] >> 32);
-        if (KW == 4) {
-            key[KW == 4 ? 2 : 0] = (uint32_t)pr.k[HI];
-            key[KW == 4 ? 3 : 0] = (uint32_t)(pr.k[HI] >> 32);
-        }
         bool done = false;
-        if (pr.hot) done = hot_add<KW>(hot_replica<KW>(p), key, pr.h, pr.b, pr.pk);
-        if (!done) table_add<KW>(p, key, pr.h, pr.b, pr.pk, 1ull);
+        if (KW <= 4 && hot)
+            done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, h, b, pk);
+        if (!done) table_add<KW>(p, key, h, b, pk, 1ull);
     }
-    pr.slot = nullptr;
+    if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
+    return (uint32_t)h;
 }
 
 // ---- tile staging: one bulk-async copy per tile ----------------------------------------------
@@ -469,6 +395,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -499,39 +426,41 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, ui
                  : "memory");
 }
 
-// Staged span of a tile whose records occupy stream bytes [b0, b1): as much as fits the buffer, starting at b0
-// rounded down to 16 (the bulk copy's alignment).  Returns the stream byte one past the staged range (= b0 & ~15
-// when nothing can be staged: insane bounds).  Records that end beyond it (oversized tiles, out-of-order offsets)
-// are parsed from global memory instead.  Stream positions fit 32 bits (offsets are u32).
-__device__ __forceinline__ uint32_t tile_staged_end(const SubmitParams &p, uint32_t b0, uint32_t b1)
-{
-    const uint32_t a0 = b0 & ~15u, base = (uint32_t)p.base, end = base + (uint32_t)p.len;
-    const bool sane = b0 <= b1 && b0 >= base && b1 <= end;
-    return a0 + (sane ? min((b1 - a0 + 15u) & ~15u, p.tile_bytes) : 0u);
-}
+struct TileInfo {
+    uint32_t r0, n;   // first record, record count
+    uint32_t b0;      // stream byte of the tile's first record
+    uint32_t a0;      // b0 rounded down to 16: stream byte of shared-memory byte 0
+    uint32_t s_end;   // stream byte one past the staged range (a0 if nothing is staged)
+};
 
-// One thread: stage tile t (records' bytes [b0, b1)) into a buffer -- the bytes AND the tile's slice of the offsets
-// array (n+1 words), two bulk copies completing on the buffer's barrier.  The copies move whole 16-byte units; the odd
-// tail of the offsets slice (one word for a full tile of 256) is stored by this thread before it arms the barrier.
-__device__ __forceinline__ void tile_issue(const SubmitParams &p, uint32_t t, uint32_t b0, uint32_t b1, uint32_t buf, uint32_t *soff,
-                                           uint2 *bounds, uint32_t bar)
+// Stage as much of the byte span of records [r0, r0+n) as fits into shared memory.
+// Records that end beyond s_end (oversized tiles, out-of-order offsets) are parsed
+// from global memory instead.
+__device__ __forceinline__ TileInfo stage_tile(const SubmitParams &p, uint32_t tile, uint8_t *smem)
 {
-    const uint32_t r0 = t * p.tile_records, n = min(p.tile_records, p.n_records - r0);
-    const uint32_t *src = p.offsets + r0;
-    const uint32_t s_end = tile_staged_end(p, b0, b1), a0 = b0 & ~15u, nbytes = s_end - a0;
-    *bounds = make_uint2(b0, s_end);
-    const uint32_t bulk_words = p.offsets_aligned ? ((n + 1u) & ~3u) : 0u;
-    for (uint32_t i = bulk_words; i < n; i++) soff[i] = __ldg(src + i);
-    soff[n] = b1;
-    // the buffer's last readers used ordinary loads; the copies write through the async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (nbytes + bulk_words) {
-        mbar_expect_tx(bar, nbytes + bulk_words * 4u);
-        if (nbytes) bulk_load(buf, p.buf + (a0 - (uint32_t)p.base), nbytes, bar);
-        if (bulk_words) bulk_load(smem_u32(soff), src, bulk_words * 4u, bar);
-    } else {
-        mbar_arrive(bar);
+    TileInfo t;
+    t.r0 = tile * p.tile_records;
+    t.n = min(p.tile_records, p.n_records - t.r0);
+    t.b0 = __ldg(p.offsets + t.r0);
+    const uint32_t b1 = __ldg(p.offsets + t.r0 + t.n);
+    t.a0 = t.b0 & ~15u;
+    const unsigned long long end = p.base + p.len;
+    const bool sane = t.b0 <= b1 && t.b0 >= p.base && (unsigned long long)b1 <= end;
+    uint32_t nbytes = 0;
+    if (sane) nbytes = min((b1 - t.a0 + 15u) & ~15u, p.tile_bytes);
+    t.s_end = t.a0 + nbytes;
+    const uint32_t bar = smem_u32(smem + p.tile_bytes + kTilePad);
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (nbytes) {
+            mbar_expect_tx(bar, nbytes);
+            bulk_load(smem_u32(smem), p.buf + ((unsigned long long)t.a0 - p.base), nbytes, bar);
+        } else {
+            mbar_arrive(bar);
+        }
     }
+    return t;
 }
 
 // ---- consumers ----------------------------------------------------------------------------------
@@ -546,8 +475,7 @@ struct Columns {
 
 struct TileParams {
     SubmitParams p;
-    Columns c;         // only read by ColConsumer
-    ShapeTable shape;  // the batch's field list, specialised to the consumer's NEED mask (decode.cuh)
+    Columns c;  // only read by ColConsumer
 };
 
 // ---- hot keys --------------------------------------------------------------------------------------
@@ -561,16 +489,17 @@ struct TileParams {
 template <int MODE, bool WEIGHTED>
 struct AggConsumer {
     static constexpr int KW = KeyTraits<MODE>::KW;
-    static constexpr int PKW = KW <= 4 ? KW : 1;  // layout of the in-flight probe (unused for wide keys)
     static constexpr uint32_t NEED = KeyTraits<MODE>::NEED | F_BYTES | F_PACKETS | (WEIGHTED ? F_SAMPLING_RATE : 0u);
+#ifndef FA_AGG_MIN_BLOCKS
+#define FA_AGG_MIN_BLOCKS 8
+#endif
+    static constexpr int MIN_BLOCKS = KW <= 4 ? FA_AGG_MIN_BLOCKS : 5;  // 32 / 48 registers per thread
     static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     static constexpr bool PERMUTE = true;                // nothing is stored per record: lanes may take any record
     struct Item {
         uint32_t h32;
         bool have;
     };
-    typedef Probe<PKW> State;
-    static __device__ __forceinline__ void state_clear(State &st) { st.slot = nullptr; }
     static __device__ __forceinline__ void item_clear(Item &it)
     {
         it.h32 = 0;
@@ -582,22 +511,20 @@ struct AggConsumer {
         const unsigned int d = __ldg(&p.counters->hint[p.hint_set ^ 1u][0]), n = __ldg(&p.counters->hint[p.hint_set ^ 1u][1]);
         return n != 0u && d * 16u >= n;  // >= 1/16 of the sampled lanes repeat
     }
-    // first half: everything up to the load of the first probe
-    static __device__ __forceinline__ void begin(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
-                                                 Item &it, State &st)
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
+                                                   Item &it)
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            it.h32 = aggregate_begin<MODE>(tp.p, f, nokey, hot, it.have, st);
+            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
     }
-    static __device__ __forceinline__ void finish(const TileParams &tp, State &st) { aggregate_finish<PKW>(tp.p, st); }
     // every 64th tile measures how often keys repeat inside a warp (feeds the next submit's decision)
-    static __device__ __forceinline__ void sample_repeats(const SubmitParams &p, uint32_t tile, const Item &it)
+    static __device__ __forceinline__ void sample_repeats(const SubmitParams &p, const Item &it)
     {
-        if (!HOT || (tile & 63u) != 0u) return;
+        if (!HOT || (blockIdx.x & 63u) != 0u) return;
         const uint32_t h32 = it.have ? it.h32 : (0x9E3779B9u * (threadIdx.x + 1u));
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h32);
         const uint32_t dups = __popc(__ballot_sync(0xFFFFFFFFu, it.have && __popc(peers) > 1));
@@ -618,15 +545,17 @@ __device__ __forceinline__ uint4 addr_bytes(const uint32_t be[4])
 
 struct ColConsumer {
     static constexpr uint32_t NEED = F_ALL;
+    static constexpr int MIN_BLOCKS = 4;  // all 16 fields live: 64 registers per thread
     static constexpr bool PERMUTE = false;  // column stores stay coalesced: lane i writes row r0+i
     struct Item {};
-    struct State {};
-    static __device__ __forceinline__ void state_clear(State &) {}
     static __device__ __forceinline__ void item_clear(Item &) {}
     static __device__ __forceinline__ bool want_hot(const SubmitParams &) { return false; }
-    static __device__ __forceinline__ void sample_repeats(const SubmitParams &, uint32_t, const Item &) {}
-    static __device__ __forceinline__ void finish(const TileParams &, State &) {}
-    static __device__ __forceinline__ void begin(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &, bool, Item &, State &)
+    static __device__ __forceinline__ void sample_repeats(const SubmitParams &, const Item &) {}
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool, Item &)
+    {
+        consume(tp, r, ok, f, bad, nokey);
+    }
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &)
     {
         const Columns &c = tp.c;
         if (!ok) {
@@ -656,28 +585,10 @@ struct ColConsumer {
     }
 };
 
-// A record the shape fast path did not decide, parsed by the order-agnostic decoder from the staged tile and consumed
-// on the spot.  Out of line with its own Flow, so the fast path keeps its Flow in registers.  Returns bad | nokey << 1.
-template <class Consumer>
-__device__ __noinline__ uint32_t record_from_tile(const TileParams &tp, uint32_t r, uint32_t smem_base, uint32_t p0, uint32_t p1, bool hot)
-{
-    uint32_t bad = 0, nokey = 0;
-    Flow f;
-    flow_reset(f);
-    SmemSrc s;
-    s.base = smem_base;
-    const bool ok = decode_record<Consumer::NEED>(s, p0, p1, tp.p.framed != 0, f);
-    typename Consumer::Item it;
-    typename Consumer::State st;
-    Consumer::item_clear(it);
-    Consumer::state_clear(st);
-    Consumer::begin(tp, r, ok, f, bad, nokey, hot, it, st);
-    Consumer::finish(tp, st);
-    return bad | (nokey << 1);
-}
-
 // one record straight from global memory (it did not fit the staged tile, or its
-// offsets are out of order): correct, slow, rare.  Returns bad | nokey << 1.
+// offsets are out of order): correct, slow, rare.  Out of line with its own Flow so
+// the hot path keeps its Flow in registers.
+// Returns bad | nokey << 1.
 template <class Consumer>
 __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32_t r, uint32_t o0, uint32_t o1)
 {
@@ -698,208 +609,74 @@ __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32
         ok = decode_record<Consumer::NEED>(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, f);
     }
     typename Consumer::Item it;
-    typename Consumer::State st;
     Consumer::item_clear(it);
-    Consumer::state_clear(st);
-    Consumer::begin(tp, r, ok, f, bad, nokey, false, it, st);
-    Consumer::finish(tp, st);
+    Consumer::consume(tp, r, ok, f, bad, nokey, false, it);
     return bad | (nokey << 1);
 }
 
-__device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad, uint32_t nokey, uint32_t slow)
+__device__ __forceinline__ void flush_counts(const SubmitParams &p, uint32_t bad, uint32_t nokey)
 {
     bad = __reduce_add_sync(0xFFFFFFFFu, bad);
     nokey = __reduce_add_sync(0xFFFFFFFFu, nokey);
-    slow = __reduce_add_sync(0xFFFFFFFFu, slow);
     if ((threadIdx.x & 31) == 0) {
         if (bad) atomicAdd(&p.counters->n_bad, (unsigned long long)bad);
         if (nokey) atomicAdd(&p.counters->n_nokey, (unsigned long long)nokey);
-        if (slow) atomicAdd(&p.counters->n_slow, (unsigned long long)slow);
     }
 }
 
 // Which record of the tile does this thread parse?  Lanes of a warp read their records from shared memory in
 // lock step, so the bank pattern is set by the byte distance between the records of neighbouring lanes.  With
 // consecutive records and near-constant record sizes that distance can resonate with the 32 x 4-byte banks
-// (measured: 86-byte records = 21.5 words, 3 lanes apart = 64.5 words -> every third lane on one bank).  Each
-// group of d = 2^shift warps therefore shares a run of 32*d records, neighbouring lanes taking records d apart;
-// d is chosen per batch from its mean record size (pick_lane_stride, host side).  A bijection on [0, kThreads).
+// (measured: 86-byte records = 21.5 words, 3 lanes apart = 64.5 words -> 3-4-way conflicts on every load, fused
+// kernel 0.87 ms instead of 0.56 ms).  Each group of d = 2^shift warps therefore shares a run of 32*d records,
+// neighbouring lanes taking records d apart; d in {1,2,4,8} is chosen per batch from its mean record size so that the
+// predicted bank multiplicity is smallest (pick_lane_stride, host side; the host passes log2 d, so no division
+// here).  A bijection on [0, THREADS).
 __device__ __forceinline__ uint32_t record_of_thread(uint32_t shift)
 {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     return ((warp >> shift) << (5u + shift)) + (lane << shift) + (warp & ((1u << shift) - 1u));
 }
 
-// ---- the stream kernel: decode (+ consume) tiles blockIdx.x, blockIdx.x + gridDim.x, ... ---------------------
-//
-// Shared memory: two tile buffers of tile_bytes + kTilePad each, two offsets slices of kStreamOffBytes, then
-// {full[2] mbarriers, readers_done[2], bounds[2], next_bounds[2][2]}.
+// ---- the tile kernel: decode (+ consume) one tile per CTA ------------------------------------
 
-template <class Consumer>
-__global__ void __launch_bounds__(kThreads, kStreamBlocksPerSM) k_stream(const __grid_constant__ TileParams tp)
+template <class Consumer, int THREADS>
+__global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / THREADS) k_tile(const __grid_constant__ TileParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const SubmitParams &p = tp.p;
-    const uint32_t buf_stride = p.tile_bytes + kTilePad;
-    uint8_t *offs_area = smem + 2u * buf_stride;                             // two offsets slices of kStreamOffBytes
-    uint8_t *ctl = offs_area + 2u * kStreamOffBytes;
-    const uint32_t bar0 = smem_u32(ctl);                                     // full[b] at bar0 + 8 b
-    unsigned int *readers_done = reinterpret_cast<unsigned int *>(ctl + 16); // [2]
-    uint2 *bounds = reinterpret_cast<uint2 *>(ctl + 32);                     // [2]: {b0, s_end} of the tile in buffer b
-    volatile uint32_t *next_bounds = reinterpret_cast<volatile uint32_t *>(ctl + 48);  // [2][2]: byte bounds of the tile to stage next in buffer b
-    const uint32_t smem0 = smem_u32(smem);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_tiles = p.n_tiles, step = gridDim.x;
-    const uint32_t n_warps = kThreads / 32;
-
-    // byte bounds of tile t's records: which = 0 the first record's start, 1 the last record's end
-    auto tile_bound = [&](uint32_t t, uint32_t which) {
-        const uint32_t r0 = t * p.tile_records, n = min(p.tile_records, p.n_records - r0);
-        return __ldg(p.offsets + r0 + (which ? n : 0u));
-    };
-    if (threadIdx.x == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8u, 1);
-        readers_done[0] = readers_done[1] = 0u;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint32_t k = 0; k < 2u; k++) {  // the first two tiles of this CTA
-            const uint32_t t = blockIdx.x + k * step;
-            if (t < n_tiles)
-                tile_issue(p, t, tile_bound(t, 0), tile_bound(t, 1), smem0 + k * buf_stride,
-                           reinterpret_cast<uint32_t *>(offs_area + k * kStreamOffBytes), bounds + k, bar0 + 8u * k);
-        }
-    }
-    __syncthreads();
-
-    const bool hot = Consumer::want_hot(p);  // uniform over the grid
-    const bool framed = p.framed != 0;
-    uint32_t bad = 0, nokey = 0, slow = 0;
+    const TileInfo t = stage_tile(p, blockIdx.x, smem);
+    const bool hot = Consumer::want_hot(p);  // uniform over the grid; the load overlaps the tile copy
+    uint32_t bad = 0, nokey = 0;
     uint32_t in_tile = threadIdx.x;
-    if (Consumer::PERMUTE && p.lane_shift) in_tile = record_of_thread(p.lane_shift);
-    typename Consumer::State state;  // the previous tile's record: its first probe is in flight during this tile's parse
-    Consumer::state_clear(state);
-
-    uint32_t k = 0;
-#pragma unroll 1
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += step, k++) {
-        const uint32_t b = k & 1u;
-        const uint32_t r0 = t * p.tile_records, n = min(p.tile_records, p.n_records - r0);
-        // short tails keep the identity mapping (the permutation is a bijection on full tiles only)
-        const uint32_t mine = n == (uint32_t)kThreads ? in_tile : threadIdx.x;
-        const bool active = mine < n;
-        const uint32_t r = r0 + mine;
-        const uint32_t *soff = reinterpret_cast<const uint32_t *>(offs_area + b * kStreamOffBytes);
-        // warp 0 fetches the byte bounds of the tile that will follow this one in buffer b (lane 0: begin, lane 1: end);
-        // they travel through shared memory to whichever warp re-arms the buffer, a whole parse later
-        const bool refill = t + 2u * step < n_tiles;
-        uint32_t nbound = 0;
-        if (refill && threadIdx.x < 2u) nbound = tile_bound(t + 2u * step, threadIdx.x);
-
-        mbar_wait(bar0 + 8u * b, (k >> 1) & 1u);
-        const uint2 bb = bounds[b];  // {b0, s_end}
-        const uint32_t o0 = active ? soff[mine] : 0u, o1 = active ? soff[mine + 1u] : 0u;
-        const uint32_t buf = smem0 + b * buf_stride, a0 = bb.x & ~15u;
-        typename Consumer::Item item;
-        Consumer::item_clear(item);
-        // every lane walks the field list (lanes without a staged record walk an empty span); cursors are absolute
-        // shared-window addresses (the buffers are 16-byte aligned, so alignment arithmetic is unchanged)
-        const bool from_tile = active && o0 >= bb.x && o0 <= o1 && o1 <= bb.y;
-        const uint32_t p0 = buf + (from_tile ? o0 - a0 : 0u), p1 = buf + (from_tile ? o1 - a0 : 0u);
-        Flow f;
-        flow_reset(f);
-        SmemSrc s;
-        s.base = 0u;
-        const bool fast = decode_record_shape<Consumer::NEED>(tp.shape, s, p0, p1, framed, f) && from_tile;
-        if (!fast && active) {  // parsed by the order-agnostic decoder and consumed on the spot
-            uint32_t res;
-            if (from_tile) {
-                slow++;
-                res = record_from_tile<Consumer>(tp, r, 0u, p0, p1, hot);
-            } else {
-                res = record_from_global<Consumer>(tp, r, o0, o1);
-            }
+    // full tiles only (the mapping is a bijection on [0, THREADS)); short tails keep the identity
+    if (Consumer::PERMUTE && p.lane_shift && t.n == (uint32_t)THREADS && (THREADS / 32) >= (1 << p.lane_shift)) in_tile = record_of_thread(p.lane_shift);
+    const bool active = in_tile < t.n;
+    const uint32_t r = t.r0 + in_tile;
+    uint32_t o0 = 0, o1 = 0;
+    if (active) {  // in flight while the bulk copy lands
+        o0 = __ldg(p.offsets + r);
+        o1 = __ldg(p.offsets + r + 1);
+    }
+    mbar_wait(smem_u32(smem + p.tile_bytes + kTilePad), 0);
+    typename Consumer::Item item;
+    Consumer::item_clear(item);
+    if (active) {
+        if (o0 >= t.b0 && o0 <= o1 && o1 <= t.s_end) {
+            Flow f;
+            flow_reset(f);
+            SmemSrc s;
+            s.base = smem_u32(smem);
+            const bool ok = decode_record<Consumer::NEED>(s, o0 - t.a0, o1 - t.a0, p.framed != 0, f);
+            Consumer::consume(tp, r, ok, f, bad, nokey, hot, item);
+        } else {
+            const uint32_t res = record_from_global<Consumer>(tp, r, o0, o1);  // updates the table itself
             bad += res & 1u;
             nokey += res >> 1;
         }
-        // this warp is done with buffer b: count it (the answer -- am I the last? -- is looked at after the table work)
-        if (refill && threadIdx.x < 2u) next_bounds[2u * b + threadIdx.x] = nbound;
-        __syncwarp();
-        unsigned int seen = 0;
-        if (lane == 0) {
-            __threadfence_block();
-            seen = atomicAdd(&readers_done[b], 1u);
-        }
-        Consumer::finish(tp, state);  // the previous tile's record: its probe has had a whole parse to come back
-        if (fast) Consumer::begin(tp, r, true, f, bad, nokey, hot, item, state);
-        Consumer::sample_repeats(p, t, item);
-        // buffer b is free once all warps are past it; the last one re-arms it with tile k+2 of this CTA
-        if (lane == 0 && seen == n_warps - 1u) {
-            readers_done[b] = 0u;
-            if (refill)
-                tile_issue(p, t + 2u * step, next_bounds[2u * b], next_bounds[2u * b + 1u], buf,
-                           reinterpret_cast<uint32_t *>(offs_area + b * kStreamOffBytes), bounds + b, bar0 + 8u * b);
-        }
     }
-    Consumer::finish(tp, state);
-    flush_counts(p, bad, nokey, slow);
-}
-
-// ---- the batch's field list ------------------------------------------------------------------------------
-//
-// 256 records spread over the batch are walked (shape_collect, decode.cuh) and every tag a fast-path step could
-// stand for is marked; the ascending list of marked tag values goes to (pinned) host memory, where the next launches
-// turn it into their ShapeTable.  Purely a speed matter: results never depend on the table.
-struct ShapeLearned {
-    uint32_t n;      // tag values written (0 when more than kShapeMax distinct tags were seen: no fast path)
-    uint32_t total;  // distinct tags seen
-    uint16_t tagval[kShapeMax];
-};
-
-struct MarkTag {
-    unsigned int *bits;  // three bitmaps of 2^14 bits: tag seen | with a 1..4-byte varint | with a 5-byte varint
-    __device__ __forceinline__ void operator()(uint32_t tagval, uint32_t vb) const
-    {
-        const uint32_t w = (tagval >> 5) & 511u, bit = 1u << (tagval & 31u);
-        atomicOr(&bits[w], bit);
-        if (vb >= 1u && vb <= 4u) atomicOr(&bits[512u + w], bit);
-        if (vb == 5u) atomicOr(&bits[1024u + w], bit);
-    }
-};
-
-__global__ void __launch_bounds__(256) k_learn_shape(const SubmitParams p, ShapeLearned *out)
-{
-    __shared__ unsigned int bits[3 * 512];  // one bit per tag value < 2^14, three times (MarkTag)
-    for (uint32_t i = threadIdx.x; i < 3u * 512u; i += blockDim.x) bits[i] = 0u;
-    __syncthreads();
-    const uint32_t n = p.n_records;
-    const uint32_t r = n >= 256u ? (uint32_t)(((unsigned long long)threadIdx.x * n) >> 8) : threadIdx.x;
-    if (r < n) {
-        const uint32_t o0 = __ldg(p.offsets + r), o1 = __ldg(p.offsets + r + 1);
-        if (o0 < o1 && o0 >= p.base && (unsigned long long)o1 <= p.base + p.len) {
-            ByteSrc s;
-            s.words = reinterpret_cast<const uint32_t *>(p.buf);
-            s.limit_word = (uint32_t)(((p.len + 15ull) & ~15ull) / 4ull) - 1u;
-            shape_collect(s, (uint32_t)(o0 - p.base), (uint32_t)(o1 - p.base), p.framed != 0, MarkTag{bits});
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t m = 0;
-        for (uint32_t w = 0; w < 512u; w++) {
-            unsigned int v = bits[w];
-            while (v) {
-                const uint32_t bit = __ffs((int)v) - 1u;
-                v &= v - 1u;
-                if (m < kShapeMax)
-                    out->tagval[m] = (uint16_t)((w * 32u + bit) | (((bits[512u + w] >> bit) & 1u) ? kTagSaw4 : 0u) |
-                                                (((bits[1024u + w] >> bit) & 1u) ? kTagSaw5 : 0u));
-                m++;
-            }
-        }
-        out->total = m;
-        out->n = m <= kShapeMax ? m : 0u;
-        __threadfence_system();
-    }
+    Consumer::sample_repeats(p, item);
+    flush_counts(p, bad, nokey);
 }
 
 // ---- kernel 2 alone: columns -> table / sketch -------------------------------------------------
@@ -936,12 +713,9 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
             f.dst_len = c.dst_addr_len[r] == 255 ? 17u : c.dst_addr_len[r];
         }
         bool have;
-        Probe<(KeyTraits<MODE>::KW <= 4 ? KeyTraits<MODE>::KW : 1)> pr;
-        pr.slot = nullptr;
-        aggregate_begin<MODE>(p, f, nokey, false, have, pr);
-        aggregate_finish(p, pr);
+        aggregate_flow<MODE>(p, f, nokey, false, have);
     }
-    flush_counts(p, 0, nokey, 0);
+    flush_counts(p, 0, nokey);
 }
 
 // ---- table reset / flush / top-K candidates ----------------------------------------------------------

@@ -57,7 +57,7 @@ class FaConfig(C.Structure):
 
 
 class FaStats(C.Structure):
-    _fields_ = [(k, C.c_uint64) for k in ("n_records", "n_bad", "n_nokey", "n_dropped", "n_groups", "n_submits", "bytes_in", "n_kernels", "n_slow", "gpu_busy_us")]
+    _fields_ = [(k, C.c_uint64) for k in ("n_records", "n_bad", "n_nokey", "n_dropped", "n_groups", "n_submits", "bytes_in", "n_kernels", "gpu_busy_us")]
 
 
 class FaMockerConfig(C.Structure):
@@ -94,7 +94,6 @@ _PROTOS = {
     "fa_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32]),
     "fa_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32]),
     "fa_sync": (C.c_int, [C.c_void_p]),
-    "fa_set_shape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "fa_stats_get": (C.c_int, [C.c_void_p, C.POINTER(FaStats)]),
     "fa_flush": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32]),
     "fa_merge_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
@@ -247,16 +246,6 @@ class FlowAgg:
 
     def sync(self):
         self._check(self._L.fa_sync(self._h), "fa_sync")
-
-    def set_shape(self, tag_values):
-        """Pin the decoder's field list (ascending field_number << 3 | wire_type); [] switches the fast path off,
-        None returns to learning it from the data.  Speed only: rows never depend on it."""
-        if tag_values is None:
-            self._check(self._L.fa_set_shape(self._h, None, 0), "fa_set_shape")
-            return
-        t = np.ascontiguousarray(np.asarray(tag_values, dtype=np.uint16))
-        keep = t if t.size else np.zeros(1, dtype=np.uint16)
-        self._check(self._L.fa_set_shape(self._h, keep.ctypes.data, t.size), "fa_set_shape")
 
     def stats(self):
         s = FaStats()

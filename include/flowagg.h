@@ -114,8 +114,6 @@ typedef struct fa_stats {
     uint64_t n_submits;  /* kernel launches of the decode/aggregate kernel */
     uint64_t bytes_in;   /* input bytes consumed */
     uint64_t n_kernels;  /* launches of the library's own CUDA kernels (all kinds) */
-    uint64_t n_slow;     /* records the decoder's lock-step fast path did not decide (parsed by the
-                            order-agnostic decoder instead; same result, ~2x the instructions)     */
     uint64_t gpu_busy_us; /* device time of the decode/aggregate kernels so far (CUDA events around
                              every launch; what a GPU-busy gauge divides by wall time)            */
 } fa_stats;
@@ -166,16 +164,6 @@ int fa_submit(fa_ctx *ctx, const uint8_t *buf, size_t len, const uint32_t *offse
  * HBM-resident leg. */
 int fa_submit_device(fa_ctx *ctx, const uint8_t *d_buf, size_t len, const uint32_t *d_offsets,
                      uint32_t n_records, uint32_t flags);
-
-/* The decoder's fast path walks the producer's FIELD LIST in lock step: every protobuf serializer (proto.Marshal,
- * mocker/mocker.go:97) writes each field at most once in ascending field-number order, so the records of a topic
- * are subsequences of one short list of tags.  By default the list is learned from the data: the first submit
- * of a context samples its batch (and waits ~20 us for the answer, once); it is re-learned in the background when
- * fa_flush / fa_stats_get see that more than 1/8 of the records since the last look needed the order-agnostic
- * decoder (fa_stats.n_slow).  This call pins the list instead: tag_values = ascending (field_number << 3 | wire_type),
- * at most 48; n = 0 with a non-NULL pointer switches the fast path off; NULL returns to learning.  Purely a speed
- * matter -- records the fast path does not take are parsed by the general decoder, rows never depend on the list. */
-int fa_set_shape(fa_ctx *ctx, const uint16_t *tag_values, uint32_t n);
 
 int fa_sync(fa_ctx *ctx); /* wait for everything submitted so far */
 int fa_stats_get(fa_ctx *ctx, fa_stats *out); /* implies fa_sync */

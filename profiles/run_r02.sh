@@ -16,7 +16,7 @@ cat gpurun_out/${TAG}_bench_first300m.json | cut -c1-600
 if [ "${3:-prof}" = "prof" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 1 --flows 33554432 --no-e2e --no-cpu > gpurun_out/${TAG}_launches_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 2 -c 2 -f -o gpurun_out/${TAG}_prof \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tile -s 2 -c 2 -f -o gpurun_out/${TAG}_prof \
       python bench.py --steps 1 --warmup 1 --flows 33554432 --no-e2e --no-cpu > gpurun_out/${TAG}_prof_bench.log 2>&1
 fi
 ls -la gpurun_out/ | grep ${TAG}

@@ -1,14 +1,14 @@
 """CPU: property tests of the decode semantics (hypothesis).  proto.Unmarshal as called at inserter/inserter.go:124 does
 not care about field order, keeps the last of repeated scalar tags, treats absent fields as zero and skips unknown
 ones; the roll-up (create.sh:92-110) is a commutative, associative sum.  Checked on the oracle AND on the device decoder
-(decode.cuh compiled for the host, shape fast path in front -- tests/decode_host)."""
+(decode.cuh compiled for the host -- tests/decode_host)."""
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
 from conftest import concat_records, frame
-from test_device_decoder_on_host import device_decode_shaped, dh, learn_shape  # noqa: F401  (dh is a fixture)
+from test_device_decoder_on_host import device_decode, dh  # noqa: F401  (dh is a fixture)
 
 # field name -> (number, is_bytes, value strategy); the 16 fields the kernels keep (pb-ext/flow.pb.go:58-143)
 U64 = st.one_of(st.integers(0, 2 ** 64 - 1), st.integers(0, 300), st.sampled_from([2 ** 28 - 1, 2 ** 28, 2 ** 32 - 1, 2 ** 32, 2 ** 35, 2 ** 63]))
@@ -69,11 +69,10 @@ def check_decodes_to(oracle, dh, msg, want):
     assert rc == 0
     for k, v in want.items():
         assert got[k] == v, (k, got[k], v, msg.hex())
-    # the device decoder, shape fast path in front (table learned from this very message), all 16 fields kept
+    # the device decoder, all 16 fields kept
     for framed in (False, True):
         blob, offs = concat_records(frame([msg]) if framed else [msg])
-        tags = learn_shape(dh, blob, offs, framed)
-        out, valid, _ = device_decode_shaped(dh, blob, offs, framed, 0, tags)
+        out, valid = device_decode(dh, blob, offs, framed, 0)
         assert valid[0]
         for k, v in want.items():
             name = {"src_addr": "src", "dst_addr": "dst", "sampler_addr": "sampler", "src_addr_len": "src_len", "dst_addr_len": "dst_len",
