@@ -129,6 +129,31 @@ def usable_cores():
     return n
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this process (and therefore the first-touch placement of the pinned host slabs it allocates afterwards) to the
+    NUMA node its GPU hangs off: on a two-socket box the H2D copies of ranks whose slabs sit on the other socket cross the
+    socket link (round 1: e2e at N=8 fell to 0.70 of linear with GPUs 4-7 on node 1).  Returns {"node": n, "cpus": k} or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                               # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def cgroup_throttle():
     """(nr_throttled, throttled_usec) of this cgroup: non-zero growth across a timed region means the box's CPU
     quota, not the GPU, stretched it."""
@@ -199,6 +224,115 @@ def run_reference(args, rank, world, emit):
     return 0
 
 
+def box_check(fp, torch, dist, dev, local_rank, rank, world, stream, slabs, n_flows, partition):
+    """The box-wide queries on the ranks' REAL tables, verified (run after the timed regions; world > 1, or --box-check).
+
+    1. exact roll-up (the SummingMergeTree merge across partitions, create.sh:88-90): every rank aggregates its whole window
+       again, then ONE hash-partitioned exchange (parallel.exchange_rows: flush, all-to-all of the rows by key owner over
+       NCCL, fa_merge_rows on the owner's GPU, flush).  Checked: the shares are disjoint by fa_row_owner, their sizes add up
+       to 65 536 groups and their counts to world x n_flows; and on a slice small enough for the CPU (2^21 flows per rank)
+       rank 0's share equals, byte for byte, the oracle's roll-up of ALL ranks' slices restricted to the keys rank 0 owns.
+    2. heavy hitters (viz-ch.json:233): a second context per rank keeps a count-min sketch (d=4, w=2^20) of SrcAddr over a
+       Zipf-addressed window of the same size; ONE all-reduce (sum, 64-bit, 32 MiB) of the sketches, then the per-rank
+       candidates ranked by the box-wide estimate and merged (parallel.box_topk).  Checked: the reduced sketch's total equals
+       the sum of the ranks' totals (linearity), no estimate is below the key's EXACT box-wide weight (exchange_rows on the
+       same table), and the top-1000 by estimate recall >= 0.99 of the exact top-1000.
+    Returns the dict that goes into the JSON line (times: CUDA events, max over ranks)."""
+    import importlib
+
+    par = importlib.import_module("flow-pipeline_b200.parallel")
+    out = {}
+
+    def dmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dsum(x):
+        t = torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return r, dmax(e0.elapsed_time(e1))
+
+    # ---- 1a. exact roll-up of the full windows
+    agg = fp.FlowAgg("aspair", device=local_rank, stream=stream, table_capacity=TABLE_CAP)
+    for (d_buf, d_off, n, nb) in slabs:
+        agg.submit_device(d_buf, d_off, n, nb)
+    share, ms = timed(lambda: par.exchange_rows(agg, device=dev))
+    out["box_flush_ms"] = ms
+    owners = fp.row_owner("aspair", share, world)
+    ok = bool((owners == rank).all()) and dsum(len(share)) == 65536 and dsum(int(share["count"].sum())) == world * n_flows
+    out["box_rollup_groups"] = dsum(len(share))
+    # ---- 1b. the same against the oracle, on a slice the CPU can do
+    m = min(1 << 21, n_flows)
+    cfg = mocker_cfg(fp, partition)
+    d_buf = torch.empty(m * 88 + 4096, dtype=torch.uint8, device=dev)
+    d_off = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    nb = agg.mocker_device(cfg, 0, m, d_buf, d_buf.numel(), d_off)
+    agg.submit_device(d_buf, d_off, m, nb)
+    share = par.exchange_rows(agg, device=dev)
+    if rank == 0:
+        from oracle import oracle as o
+
+        o.use_native()
+        parts = [o.mocker_host(seed=1 + (partition - rank + r), first=0, n=m, **MOCKER) for r in range(world)]
+        want, _ = o.run_slabs(parts, framed=True, key_mode="aspair", threads=usable_cores())
+        want = want[fp.row_owner("aspair", want, world) == 0]
+        ok = ok and bool(np.array_equal(share, want))
+        out["box_rollup_oracle_slice"] = f"{world} x {m} flows: rank 0's share ({len(share)} rows) == oracle rows it owns"
+    agg.close()
+    out["box_rollup"] = "ok" if dsum(0 if ok else 1) == 0 else "MISMATCH"
+
+    # ---- 2. sketch all-reduce + box-wide top-K on a Zipf-addressed window
+    K = 1000
+    zcfg = fp.FaMockerConfig.make(seed=101 + partition, addr_mode=fp.FA_ADDR_ZIPF24, **MOCKER)
+    aggc = fp.FlowAgg("srcaddr", device=local_rank, stream=stream, table_capacity=1 << 25, cms=True, cms_depth=4, cms_width_log2=20)
+    done = 0
+    while done < n_flows:
+        n = min(SLAB, n_flows - done)
+        nbz = aggc.mocker_device(zcfg, done, n, slabs[0][0], slabs[0][0].numel(), slabs[0][1])  # reuse one slab's memory
+        aggc.submit_device(slabs[0][0], slabs[0][1], n, nbz)
+        aggc.sync()
+        done += n
+    local, glob = par.sketch_tensor(aggc, fp.FA_CMS_LOCAL), par.sketch_tensor(aggc, fp.FA_CMS_GLOBAL)
+    aggc.sync()
+    _, ms = timed(lambda: par.allreduce_sketch(local, glob))
+    out["sketch_allreduce_ms"] = ms
+    out["sketch_allreduce_bytes"] = int(local.numel() * 8)
+    tot_local = torch.tensor([int(local.sum().item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_local, op=dist.ReduceOp.SUM)
+    lin = int(tot_local.item()) == int(glob.sum().item())                       # int64 wrap-around on both sides
+    top, ms = timed(lambda: par.box_topk(aggc, K))
+    out["box_topk_ms"] = ms
+    # exact box-wide weights of the same keys: the candidate table holds sum(Bytes*SamplingRate) per key and rank
+    share = par.exchange_rows(aggc, device=dev)                                 # this rank's keys, exact box-wide sums
+    mine = share[np.argsort(share["bytes"], kind="stable")[::-1][:K]]
+    exact = par.merge_rows(mine, 4, device=dev)                                 # every rank's local top-K of its OWN keys, gathered
+    exact = exact[np.argsort(exact["bytes"], kind="stable")[::-1][:K]]
+    ex = {tuple(r["key"][:4]): int(r["bytes"]) for r in exact}
+    hits = sum(1 for r in top if tuple(r["key"][:4]) in ex)
+    under = sum(1 for r in top if tuple(r["key"][:4]) in ex and int(r["estimate"]) < ex[tuple(r["key"][:4])])
+    out["box_topk_recall"] = hits / max(len(ex), 1)
+    out["box_topk"] = "ok" if (lin and under == 0 and len(top) == K and hits >= 0.99 * len(ex)) else "MISMATCH"
+    out["box_topk_distinct_keys_box_wide"] = dsum(len(share))
+    aggc.close()
+    out["box_check"] = "ok" if out["box_rollup"] == "ok" and out["box_topk"] == "ok" else "MISMATCH"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +342,7 @@ def main():
     ap.add_argument("--flows", type=int, default=N_FLOWS, help=argparse.SUPPRESS)  # smaller runs under ncu only
     ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--box-check", action="store_true", help=argparse.SUPPRESS)  # run the box-wide queries at N=1 too
     ap.add_argument("--partition", type=int, default=None, help=argparse.SUPPRESS)  # which producer instance (default: rank)
     ap.add_argument("--first", type=int, default=0, help=argparse.SUPPRESS)  # first SequenceNum (>= 2^28: 5-byte varints, 86-byte records)
     args = ap.parse_args()
@@ -233,6 +368,7 @@ def main():
     if not torch.cuda.is_available():
         emit({"error": "no CUDA device; libflowagg has no CPU fallback"})
         return 1
+    numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -264,6 +400,17 @@ def main():
     rows_pin = torch.empty(70_000 * fp.ROW_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
     rows_out = rows_pin.numpy().view(fp.ROW_DTYPE)
 
+    # A step = the fused kernel over every slab of the window + the window's flush.  The flush is asynchronous
+    # (fa_flush_begin / fa_flush_end): the filled table is swapped for an empty one and drained on the library's side stream
+    # while the NEXT window's kernels already run; its rows are collected after those kernels have been enqueued.  Every
+    # window's rows are collected inside the timed region (the last one by drain() before the closing event).
+    pending = [False]
+
+    def collect(a):
+        rows_prev = a.flush_end(out=rows_out) if pending[0] else None
+        pending[0] = False
+        return rows_prev
+
     def step_device(per_launch=None):
         t_a = time.perf_counter()
         for (d_buf, d_off, n, nb) in slabs:
@@ -275,11 +422,16 @@ def main():
                 e1.record()
                 per_launch.append((e0, e1, nb + 4 * (n + 1)))
         t_b = time.perf_counter()
-        out_rows = agg.flush(out=rows_out)
+        rows_prev = collect(agg)       # the previous window's rows: drained while the kernels above were being enqueued / run
+        agg.flush_begin()              # this window: swap tables, drain on the side stream
+        pending[0] = True
         if dbg is not None and per_launch is not None:
             dbg["submit_s"] += t_b - t_a
             dbg["flush_s"] += time.perf_counter() - t_b
-        return out_rows
+        return rows_prev
+
+    def check_rows(rows_prev):
+        assert rows_prev is None or (int(rows_prev["count"].sum()) == n_flows and len(rows_prev) == 65536)
 
     def barrier():
         if world > 1:
@@ -293,9 +445,9 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         time.sleep(1.0)
-    rows = None
     for _ in range(args.warmup):
-        rows = step_device()
+        check_rows(step_device())
+    rows = collect(agg)
     assert rows is not None and int(rows["count"].sum()) == n_flows and len(rows) == 65536
     launches0 = agg.stats()["n_kernels"]
     barrier()
@@ -305,8 +457,9 @@ def main():
     step_wall, throttle0 = [], cgroup_throttle()
     for _ in range(args.steps):
         t_s = time.perf_counter()
-        rows = step_device(per_launch)
-        step_wall.append(1e3 * (time.perf_counter() - t_s))  # every step ends in the flush's sync
+        check_rows(step_device(per_launch))
+        step_wall.append(1e3 * (time.perf_counter() - t_s))
+    rows = collect(agg)  # the last window's rows: inside the timed region
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
@@ -317,7 +470,7 @@ def main():
                                   "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
         except Exception as ex:
             smi = str(ex)
-        print(f"[bench debug] rank {rank}: fused kernel avg {k_avg:.4f} ms/launch; idle-after-run nvidia-smi: {smi}", file=sys.stderr, flush=True)
+        print(f"[bench debug] rank {rank}: fused kernel avg {k_avg:.4f} ms/launch; numa binding {numa}; idle-after-run nvidia-smi: {smi}", file=sys.stderr, flush=True)
         print(f"[bench debug] rank {rank}: per-step wall ms {[round(x, 2) for x in step_wall]}; cgroup throttle (periods, usec) "
               f"{cgroup_throttle()} <- {throttle0}; usable cores {usable_cores()}", file=sys.stderr, flush=True)
         print(f"[bench debug] rank {rank}: {ms / args.steps:.3f} ms/step; host time per step: submits {1e3 * dbg['submit_s'] / args.steps:.3f} ms, "
@@ -352,19 +505,24 @@ def main():
         def step_e2e():
             for (hb, ho, n, nb) in hslabs:
                 eagg.submit(hb, ho, framed=True, n_records=n, nbytes=nb)
-            return eagg.flush(out=rows_out)
+            rows_prev = collect(eagg)
+            eagg.flush_begin()
+            pending[0] = True
+            return rows_prev
 
         for _ in range(args.warmup):
-            erows = step_e2e()
-        erows = erows.copy()
+            check_rows(step_e2e())
+        erows = collect(eagg).copy()
         assert np.array_equal(erows, rows)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            erows = step_e2e()
+            check_rows(step_e2e())
+        erows = collect(eagg)  # the last window's rows are read back inside the timed region
         e1.record()
         barrier()
+        assert np.array_equal(erows, rows)
         ems = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ems], dtype=torch.float64, device=dev)
@@ -373,7 +531,7 @@ def main():
         e2e = {"value": world * n_flows * args.steps / (ems * 1e-3), "unit": "flows/s",
                "h2d_bytes_per_step": int(in_bytes + 4 * (n_flows + len(slabs))), "d2h_bytes_per_step": int(rows.nbytes),
                "ms_per_step": ems / args.steps,
-               "note": "pinned host buffers -> fa_submit (64 MiB batches, copy/compute overlapped) -> fa_flush rows into a pinned host array"}
+               "note": "pinned host buffers -> fa_submit (64 MiB batches, copy/compute overlapped) -> fa_flush_begin/_end rows into a host array"}
         eagg.close()
         del hslabs
 
@@ -406,15 +564,22 @@ def main():
                "single_thread_value": m1 / c1res["seconds"]}
         del hs
 
+    # ---- box-wide queries over all ranks, verified (the collectives of this path happen at query time only) ----
+    box = None
+    if world > 1 or args.box_check:
+        box = box_check(fp, torch, dist, dev, local_rank, rank, world, stream, slabs, n_flows, partition)
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "flows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": bench_config(),
-            "detail": {"flows_per_timed_step": n_flows, "input_bytes_per_step_per_gpu": int(in_bytes), "slab_records": SLAB,
+            "detail": {"flows_per_timed_step": n_flows, "input_bytes_per_step_per_gpu": int(in_bytes), "slab_records": SLAB, "numa_rank0": numa,
                        "l2": "inputs (8.4 GB) larger than L2, streamed with L2 evict-first; the 16 MiB group table stays L2-resident by design", "table_slots": TABLE_CAP,
-                       "step": "fused decode+aggregate of every slab + flush (replica fold, compact, ORDER BY on the device, rows D2H)",
+                       "step": "fused decode+aggregate of every slab + the window's flush (replica fold, table swap, then compact / ORDER BY on the "
+                               "device / rows D2H on the library's side stream, overlapping the next window's kernels; every window's rows are "
+                               "collected inside the timed region)",
                        "box_merge": "per-rank roll-ups; the cross-rank row merge happens per 5-minute flush, outside the timed region"},
             "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak,
                          "traffic": ncu_traffic(), "kernel": "k_tile<AggConsumer<ASPAIR>> (fused decode+aggregate)",
@@ -422,6 +587,8 @@ def main():
                          "launches_timed": len(k_ms), "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         }
+        if box is not None:
+            out.update(box)
         emit(out)
     agg.close()
     if world > 1:

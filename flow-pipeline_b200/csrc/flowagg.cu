@@ -53,6 +53,21 @@ struct fa_ctx {
     size_t cms_words = 0;
     Counters *d_counters = nullptr;
     Counters *h_counters = nullptr;  // pinned
+    TableState *d_ts = nullptr;      // state of the table behind d_slots
+    TableState *h_ts = nullptr;      // pinned: last snapshot of the current table's state
+    TableState *h_ts_drain = nullptr; // pinned: state of the table an asynchronous flush is draining
+
+    // asynchronous flush (fa_flush_begin / fa_flush_end): the filled table is swapped for a spare, empty one and drained
+    // on a side stream while the next submits already fill the spare
+    uint8_t *d_slots_spare = nullptr;
+    TableState *d_ts_spare = nullptr;
+    cudaStream_t flush_stream = nullptr;
+    cudaEvent_t ev_swap = nullptr, ev_flush_done = nullptr, ev_spare_ready = nullptr;
+    void *d_fscratch = nullptr;  // the drain's own scratch (d_scratch belongs to the submit / query paths)
+    size_t fscratch_bytes = 0;
+    bool flush_pending = false, flush_deferred = false;
+    uint32_t flush_flags = 0, flush_m = 0;          // flags of the pending flush; rows the drain sorted and copied
+    fa_row *flush_rows_in = nullptr;                // every compacted row of the drained table (device, in d_fscratch)
 
     // host-submit staging (double buffered)
     uint8_t *d_stage[2] = {nullptr, nullptr};
@@ -135,19 +150,20 @@ static int ensure_scratch(fa_ctx *c, size_t bytes)
     return FA_OK;
 }
 
+// empty `slots` (capacity + 1 of them) on `stream`; with_hot: the hot-key replicas too
 template <int KW>
-static cudaError_t launch_table_init(fa_ctx *c)
+static cudaError_t launch_table_init(fa_ctx *c, uint8_t *slots, cudaStream_t stream, bool with_hot)
 {
     const unsigned long long n_slots = c->capacity + 1;
     const unsigned long long words = n_slots * (SlotLayout<KW>::BYTES / 8);
     const int grid = (int)std::min<unsigned long long>((words + 255) / 256, (unsigned long long)c->num_sms * 32);
-    k_table_init<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots);
+    k_table_init<KW><<<grid, 256, 0, stream>>>(slots, n_slots);
     c->n_kernels++;
-    if (c->d_hot) {
-        k_table_init<KW><<<c->num_sms, 256, 0, c->stream>>>(c->d_hot, (unsigned long long)kHotReplicas * kHotSlots);
+    if (with_hot && c->d_hot) {
+        k_table_init<KW><<<c->num_sms, 256, 0, stream>>>(c->d_hot, (unsigned long long)kHotReplicas * kHotSlots);
         c->n_kernels++;
+        c->hot_dirty = false;
     }
-    c->hot_dirty = false;
     return cudaGetLastError();
 }
 
@@ -156,6 +172,7 @@ static void fill_table_params(fa_ctx *c, SubmitParams &p)
     p.slots = c->d_slots;
     p.slot_mask = (uint32_t)(c->capacity - 1);
     p.counters = c->d_counters;
+    p.tstate = c->d_ts;
     p.hot_slots = c->d_hot;
 }
 
@@ -185,19 +202,20 @@ static int merge_hot(fa_ctx *c)
 }
 
 // empty table: all-ones keys (CAS layouts) / state 0 (wide keys), zero sums
-static int table_init(fa_ctx *c)
+static int table_init_at(fa_ctx *c, uint8_t *slots, cudaStream_t stream, bool with_hot)
 {
-    if (!c->d_slots) return FA_OK;
+    if (!slots) return FA_OK;
     cudaError_t e;
     switch (c->kw) {
-    case 1: e = launch_table_init<1>(c); break;
-    case 2: e = launch_table_init<2>(c); break;
-    case 4: e = launch_table_init<4>(c); break;
-    default: e = launch_table_init<11>(c); break;
+    case 1: e = launch_table_init<1>(c, slots, stream, with_hot); break;
+    case 2: e = launch_table_init<2>(c, slots, stream, with_hot); break;
+    case 4: e = launch_table_init<4>(c, slots, stream, with_hot); break;
+    default: e = launch_table_init<11>(c, slots, stream, with_hot); break;
     }
     FA_CUDA(c, e);
     return FA_OK;
 }
+static int table_init(fa_ctx *c) { return table_init_at(c, c->d_slots, c->stream, true); }
 
 extern "C" void fa_destroy(fa_ctx *c)
 {
@@ -211,6 +229,16 @@ extern "C" void fa_destroy(fa_ctx *c)
     cudaFree(c->d_cms_global);
     cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
+    if (c->flush_stream) cudaStreamSynchronize(c->flush_stream);
+    cudaFree(c->d_ts);
+    cudaFree(c->d_ts_spare);
+    cudaFreeHost(c->h_ts);
+    cudaFree(c->d_slots_spare);
+    cudaFree(c->d_fscratch);
+    if (c->ev_swap) cudaEventDestroy(c->ev_swap);
+    if (c->ev_flush_done) cudaEventDestroy(c->ev_flush_done);
+    if (c->ev_spare_ready) cudaEventDestroy(c->ev_spare_ready);
+    if (c->flush_stream) cudaStreamDestroy(c->flush_stream);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_stage[i]);
         cudaFree(c->d_stage_off[i]);
@@ -325,6 +353,11 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     // it had to be; not combining hot keys would be several times slower)
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     FA_CUDA(c, cudaHostAlloc(&c->h_counters, sizeof(Counters), cudaHostAllocDefault));
+    FA_CUDA(c, cudaMalloc(&c->d_ts, sizeof(TableState)));
+    FA_CUDA(c, cudaMemsetAsync(c->d_ts, 0, sizeof(TableState), c->stream));
+    FA_CUDA(c, cudaHostAlloc(&c->h_ts, 2 * sizeof(TableState), cudaHostAllocDefault));
+    memset(c->h_ts, 0, 2 * sizeof(TableState));
+    c->h_ts_drain = c->h_ts + 1;
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
         FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
         if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * kHotSlots * c->slot_bytes));
@@ -645,9 +678,11 @@ extern "C" int fa_sync(fa_ctx *c)
     return FA_OK;
 }
 
+// context counters and the CURRENT table's state -> h_counters / h_ts
 static int read_counters(fa_ctx *c)
 {
     FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaMemcpyAsync(c->h_ts, c->d_ts, sizeof(TableState), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));
     return FA_OK;
 }
@@ -664,8 +699,8 @@ extern "C" int fa_stats_get(fa_ctx *c, fa_stats *out)
     out->n_records = c->n_records;
     out->n_bad = c->h_counters->n_bad;
     out->n_nokey = c->h_counters->n_nokey;
-    out->n_dropped = c->h_counters->n_dropped;
-    out->n_groups = c->h_counters->n_groups;
+    out->n_dropped = c->h_ts->n_dropped;
+    out->n_groups = c->h_ts->n_groups;
     out->n_submits = c->n_submits;
     out->bytes_in = c->bytes_in;
     out->n_kernels = c->n_kernels;
@@ -683,7 +718,7 @@ static cudaError_t launch_compact(fa_ctx *c, fa_row *d_rows, unsigned long long 
 {
     const unsigned long long n_slots = c->capacity + 1;  // + the side slot
     const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
-    k_compact_rows<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, d_rows, cap, c->d_counters);
+    k_compact_rows<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, d_rows, cap, c->d_ts);
     c->n_kernels++;
     return cudaGetLastError();
 }
@@ -694,7 +729,7 @@ static cudaError_t launch_estimate(fa_ctx *c, const unsigned long long *cms, fa_
     const unsigned long long n_slots = c->capacity + 1;
     const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
     k_estimate<KW><<<grid, 256, 0, c->stream>>>(c->d_slots, n_slots, cms, c->cfg.cms_depth, c->cfg.cms_width_log2, d_out, cap,
-                                                c->d_counters);
+                                                c->d_ts);
     c->n_kernels++;
     return cudaGetLastError();
 }
@@ -711,9 +746,9 @@ static int reset_table(fa_ctx *c)
 {
     int rc = table_init(c);
     if (rc) return rc;
-    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->n_groups, 0, 8, c->stream));
-    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->n_dropped, 0, 8, c->stream));
-    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->side_state, 0, 4, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_ts->n_groups, 0, 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_ts->n_dropped, 0, 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_ts->side_state, 0, 4, c->stream));
     return FA_OK;
 }
 
@@ -729,7 +764,7 @@ __global__ void k_sort_key(const fa_row *rows, const uint32_t *perm, uint32_t n,
     if (i < n) keys[i] = rows[perm[i]].key[word];
 }
 // speculative variant: only the first counters->flush_rows rows exist; the rest of [0,n) sorts to the end
-__global__ void k_sort_key_guarded(const fa_row *rows, const uint32_t *perm, uint32_t n, int word, uint32_t *keys, const Counters *counters)
+__global__ void k_sort_key_guarded(const fa_row *rows, const uint32_t *perm, uint32_t n, int word, uint32_t *keys, const TableState *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -808,7 +843,7 @@ static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uin
     uint32_t *keys_a = (uint32_t *)(base + in_b + out_b), *keys_b = (uint32_t *)(base + in_b + out_b + u32_b);
     uint32_t *perm_a = (uint32_t *)(base + in_b + out_b + 2 * u32_b), *perm_b = (uint32_t *)(base + in_b + out_b + 3 * u32_b);
     void *cub_tmp = base + in_b + out_b + 4 * u32_b;
-    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_ts->flush_rows, 0, 8, c->stream));
     cudaError_t e;
 #define CALL_COMPACT(K) launch_compact<K>(c, rows_in, all_rows)
     FA_DISPATCH_KW(c->kw, CALL_COMPACT)
@@ -818,7 +853,7 @@ static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uin
     k_iota<<<g, 256, 0, c->stream>>>(perm_a, m);
     c->n_kernels++;
     for (int w = c->kw - 1; w >= 0; w--) {
-        k_sort_key_guarded<<<g, 256, 0, c->stream>>>(rows_in, perm_a, m, w, keys_a, c->d_counters);
+        k_sort_key_guarded<<<g, 256, 0, c->stream>>>(rows_in, perm_a, m, w, keys_a, c->d_ts);
         c->n_kernels++;
         FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, perm_a, perm_b, (int)m, 0, 32, c->stream));
         std::swap(perm_a, perm_b);
@@ -843,9 +878,10 @@ static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uin
         dst = c->h_bounce;
     }
     FA_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    FA_CUDA(c, cudaMemcpyAsync(c->h_ts, c->d_ts, sizeof(TableState), cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaMemcpyAsync(dst, rows_out, bytes, cudaMemcpyDeviceToHost, c->stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));  // the one wait
-    const uint64_t groups = c->h_counters->n_groups, dropped = c->h_counters->n_dropped;
+    const uint64_t groups = c->h_ts->n_groups, dropped = c->h_ts->n_dropped;
     if (groups > m) {  // the roll-up grew by more than 1/8: every row is still in scratch, the exact path takes over
         c->last_groups = groups;
         return FA_OK;
@@ -861,9 +897,194 @@ static int flush_speculative(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uin
     return dropped ? FA_ERR_TABLE_FULL : FA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// asynchronous flush: swap tables, drain the filled one on a side stream
+// ---------------------------------------------------------------------------------------------
+//
+// (*state).flush holds the inserter's global mutex while it talks to the database (inserter.go:90-111), so buffer()
+// stalls behind every flush.  Here the flush must not stall the stream either: fa_flush_begin folds the hot-key replicas,
+// swaps the filled table for a spare, empty one -- the very next fa_submit already aggregates into the spare -- and
+// enqueues compaction, ORDER BY, the copies to pinned host memory and the emptying of the old table on the context's
+// flush stream; fa_flush_end waits for that (a blocking, non-spinning event wait) and hands the rows over.
+
+template <int KW>
+static cudaError_t launch_compact_at(fa_ctx *c, const uint8_t *slots, TableState *ts, fa_row *d_rows, unsigned long long cap, cudaStream_t st)
+{
+    const unsigned long long n_slots = c->capacity + 1;  // + the side slot
+    const int grid = (int)std::min<uint64_t>((c->capacity + 255) / 256, (uint64_t)c->num_sms * 16);
+    k_compact_rows<KW><<<grid, 256, 0, st>>>(slots, n_slots, d_rows, cap, ts);
+    c->n_kernels++;
+    return cudaGetLastError();
+}
+
+static bool flush_async_ok(const fa_ctx *c) { return c->d_slots && c->capacity + 1 <= (1ull << 22); }
+
+// ORDER BY of the first min(m, ts->flush_rows) rows of rows_in into rows_out, on `st` (stable LSD radix sort over the
+// key words, last word first; entries past the true row count sort to the end and are never read)
+static int sort_rows_guarded(fa_ctx *c, cudaStream_t st, const fa_row *rows_in, fa_row *rows_out, uint32_t m, const TableState *ts, uint8_t *work,
+                             size_t cub_bytes)
+{
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t u32_b = al((size_t)m * 4);
+    uint32_t *keys_a = (uint32_t *)work, *keys_b = (uint32_t *)(work + u32_b);
+    uint32_t *perm_a = (uint32_t *)(work + 2 * u32_b), *perm_b = (uint32_t *)(work + 3 * u32_b);
+    void *cub_tmp = work + 4 * u32_b;
+    const int g = (int)((m + 255) / 256);
+    k_iota<<<g, 256, 0, st>>>(perm_a, m);
+    c->n_kernels++;
+    for (int w = c->kw - 1; w >= 0; w--) {
+        k_sort_key_guarded<<<g, 256, 0, st>>>(rows_in, perm_a, m, w, keys_a, ts);
+        c->n_kernels++;
+        FA_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, keys_a, keys_b, perm_a, perm_b, (int)m, 0, 32, st));
+        std::swap(perm_a, perm_b);
+    }
+    k_gather_rows<<<g, 256, 0, st>>>(rows_in, perm_a, m, rows_out);
+    c->n_kernels++;
+    FA_CUDA(c, cudaGetLastError());
+    return FA_OK;
+}
+
+extern "C" int fa_flush_begin(fa_ctx *c, uint32_t flags)
+{
+    if (!c || !c->d_slots || c->flush_pending) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    c->flush_flags = flags;
+    if ((flags & (FA_FLUSH_KEEP | FA_FLUSH_UNSORTED)) || !flush_async_ok(c)) {
+        // peeks, unsorted dumps and huge tables are drained by fa_flush_end itself, in place
+        c->flush_pending = c->flush_deferred = true;
+        return FA_OK;
+    }
+    if (!c->flush_stream) {
+        // highest priority: the drain's small kernels must slip in between the CTAs of the fused kernels that are filling
+        // the spare table (those retire every few microseconds), not wait for a whole kernel to end
+        int prio_lo = 0, prio_hi = 0;
+        FA_CUDA(c, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        FA_CUDA(c, cudaStreamCreateWithPriority(&c->flush_stream, cudaStreamNonBlocking, prio_hi));
+        FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_swap, cudaEventDisableTiming));
+        FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_spare_ready, cudaEventDisableTiming));
+        FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_flush_done, cudaEventDisableTiming | cudaEventBlockingSync));
+        FA_CUDA(c, cudaMalloc(&c->d_slots_spare, (c->capacity + 1) * c->slot_bytes));
+        FA_CUDA(c, cudaMalloc(&c->d_ts_spare, sizeof(TableState)));
+        FA_CUDA(c, cudaMemsetAsync(c->d_ts_spare, 0, sizeof(TableState), c->flush_stream));
+        int rc0 = table_init_at(c, c->d_slots_spare, c->flush_stream, false);
+        if (rc0) return rc0;
+        FA_CUDA(c, cudaEventRecord(c->ev_spare_ready, c->flush_stream));
+    }
+    int rc = merge_hot(c);  // on the main stream, into the table about to be drained
+    if (rc) return rc;
+    // rows to sort and copy: a 5-minute roll-up has about as many groups as the last one; compaction keeps EVERY row in
+    // scratch, so a wrong guess loses nothing (fa_flush_end re-sorts the exact count)
+    const uint64_t all_rows = c->capacity + 1;
+    const uint32_t m = (uint32_t)std::min<uint64_t>(all_rows, c->last_groups ? c->last_groups + c->last_groups / 8 + 256 : all_rows);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (int)all_rows, 0, 32, c->flush_stream);
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t in_b = al(all_rows * sizeof(fa_row)), work_b = 4 * al(all_rows * 4) + al(cub_bytes);
+    const size_t need = 2 * in_b + work_b;
+    if (need > c->fscratch_bytes) {
+        FA_CUDA(c, cudaStreamSynchronize(c->flush_stream));
+        if (c->d_fscratch) cudaFree(c->d_fscratch);
+        c->d_fscratch = nullptr;
+        c->fscratch_bytes = 0;
+        FA_CUDA(c, cudaMalloc(&c->d_fscratch, need));
+        c->fscratch_bytes = need;
+    }
+    const size_t host_b = (size_t)all_rows * sizeof(fa_row);
+    if (host_b > c->bounce_bytes) {
+        if (c->h_bounce) cudaFreeHost(c->h_bounce);
+        c->h_bounce = nullptr;
+        c->bounce_bytes = 0;
+        FA_CUDA(c, cudaHostAlloc(&c->h_bounce, host_b, cudaHostAllocDefault));
+        c->bounce_bytes = host_b;
+    }
+    uint8_t *base = (uint8_t *)c->d_fscratch;
+    fa_row *rows_in = (fa_row *)base, *rows_out = (fa_row *)(base + in_b);
+    // swap: the spare (emptied by the previous drain) takes over
+    FA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_spare_ready, 0));
+    FA_CUDA(c, cudaEventRecord(c->ev_swap, c->stream));
+    uint8_t *old_slots = c->d_slots;
+    TableState *old_ts = c->d_ts;
+    c->d_slots = c->d_slots_spare;
+    c->d_ts = c->d_ts_spare;
+    c->d_slots_spare = old_slots;
+    c->d_ts_spare = old_ts;
+    // the drain
+    cudaStream_t fs = c->flush_stream;
+    FA_CUDA(c, cudaStreamWaitEvent(fs, c->ev_swap, 0));
+    FA_CUDA(c, cudaMemsetAsync(&old_ts->flush_rows, 0, 8, fs));
+    cudaError_t e;
+#define CALL_COMPACT(K) launch_compact_at<K>(c, old_slots, old_ts, rows_in, all_rows, fs)
+    FA_DISPATCH_KW(c->kw, CALL_COMPACT)
+#undef CALL_COMPACT
+    FA_CUDA(c, e);
+    rc = sort_rows_guarded(c, fs, rows_in, rows_out, m, old_ts, base + 2 * in_b, cub_bytes);
+    if (rc) return rc;
+    FA_CUDA(c, cudaMemcpyAsync(c->h_ts_drain, old_ts, sizeof(TableState), cudaMemcpyDeviceToHost, fs));
+    FA_CUDA(c, cudaMemcpyAsync(c->h_bounce, rows_out, (size_t)m * sizeof(fa_row), cudaMemcpyDeviceToHost, fs));
+    rc = table_init_at(c, old_slots, fs, false);
+    if (rc) return rc;
+    FA_CUDA(c, cudaMemsetAsync(old_ts, 0, sizeof(TableState), fs));
+    FA_CUDA(c, cudaEventRecord(c->ev_spare_ready, fs));
+    FA_CUDA(c, cudaEventRecord(c->ev_flush_done, fs));
+    c->flush_m = m;
+    c->flush_rows_in = rows_in;
+    c->flush_pending = true;
+    c->flush_deferred = false;
+    return FA_OK;
+}
+
+static int flush_sync(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags);
+
+extern "C" int fa_flush_end(fa_ctx *c, fa_row *rows, size_t cap, size_t *n)
+{
+    if (!c || !n || !c->flush_pending) return FA_ERR_INVALID;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (c->flush_deferred) {
+        const int rc = flush_sync(c, rows, cap, n, c->flush_flags);
+        if (rc != FA_ERR_CAPACITY) c->flush_pending = c->flush_deferred = false;
+        return rc;
+    }
+    FA_CUDA(c, cudaEventSynchronize(c->ev_flush_done));  // blocking wait: the host thread sleeps, it does not spin
+    const uint64_t groups = c->h_ts_drain->n_groups, dropped = c->h_ts_drain->n_dropped;
+    *n = (size_t)groups;
+    if (groups > cap || (groups && !rows)) return FA_ERR_CAPACITY;  // the rows stay in scratch: call again with a larger array
+    if (groups > c->flush_m) {
+        // the roll-up grew by more than 1/8 since the last flush: every row is still in scratch, order the exact count
+        const uint32_t m = (uint32_t)groups;
+        size_t cub_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (int)(c->capacity + 1), 0, 32, c->flush_stream);
+        auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t in_b = al((c->capacity + 1) * sizeof(fa_row));
+        uint8_t *base = (uint8_t *)c->d_fscratch;
+        fa_row *rows_out = (fa_row *)(base + in_b);
+        // the drained table's state was zeroed; the guard needs the row count again
+        TableState tmp{};
+        tmp.flush_rows = groups;
+        FA_CUDA(c, cudaMemcpyAsync(c->d_ts_spare, &tmp, sizeof tmp, cudaMemcpyHostToDevice, c->flush_stream));
+        int rc = sort_rows_guarded(c, c->flush_stream, c->flush_rows_in, rows_out, m, c->d_ts_spare, base + 2 * in_b, cub_bytes);
+        if (rc) return rc;
+        FA_CUDA(c, cudaMemcpyAsync(c->h_bounce, rows_out, (size_t)m * sizeof(fa_row), cudaMemcpyDeviceToHost, c->flush_stream));
+        FA_CUDA(c, cudaMemsetAsync(c->d_ts_spare, 0, sizeof(TableState), c->flush_stream));
+        FA_CUDA(c, cudaEventRecord(c->ev_spare_ready, c->flush_stream));
+        FA_CUDA(c, cudaStreamSynchronize(c->flush_stream));
+    }
+    if (groups) memcpy(rows, c->h_bounce, (size_t)groups * sizeof(fa_row));
+    c->last_groups = groups;
+    c->flush_pending = false;
+    return dropped ? FA_ERR_TABLE_FULL : FA_OK;
+}
+
 extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
 {
-    if (!c || !n || !c->d_slots) return FA_ERR_INVALID;
+    if (!c || !n || !c->d_slots || c->flush_pending) return FA_ERR_INVALID;
+    return flush_sync(c, rows, cap, n, flags);
+}
+
+// the synchronous flush: everything on the context's own stream, in place
+static int flush_sync(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
+{
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
     static const bool dbg = getenv("FA_DEBUG_FLUSH") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -885,8 +1106,8 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
     // exact path: two synchronisations, one to learn the row count, one for the rows
     rc = read_counters(c);
     if (rc) return rc;
-    const uint64_t groups = c->h_counters->n_groups;
-    const uint64_t dropped = c->h_counters->n_dropped;
+    const uint64_t groups = c->h_ts->n_groups;
+    const uint64_t dropped = c->h_ts->n_dropped;
     c->last_groups = groups;
     const auto t_count = now();
     *n = (size_t)groups;
@@ -895,7 +1116,7 @@ extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t
     if (groups) {
         rc = ensure_scratch(c, groups * sizeof(fa_row));
         if (rc) return rc;
-        FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+        FA_CUDA(c, cudaMemsetAsync(&c->d_ts->flush_rows, 0, 8, c->stream));
         cudaError_t e;
 #define CALL_COMPACT(K) launch_compact<K>(c, (fa_row *)c->d_scratch, groups)
         FA_DISPATCH_KW(c->kw, CALL_COMPACT)
@@ -974,6 +1195,7 @@ static int add_rows_device(fa_ctx *c, const fa_row *d_rows, size_t n, uint32_t o
 
 extern "C" int fa_merge_rows(fa_ctx *c, const fa_row *rows, size_t n, uint32_t owner, uint32_t n_owners)
 {
+    if (c && c->flush_pending) return FA_ERR_INVALID;  // fa_flush_end first
     if (!c || !c->d_slots || (n && !rows) || (n_owners > 1 && owner >= n_owners)) return FA_ERR_INVALID;
     if (!n) return FA_OK;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
@@ -1055,7 +1277,7 @@ extern "C" int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t
 {
     if (!ctxs || n_ctx < 1 || !n || (flags & FA_FLUSH_KEEP)) return FA_ERR_INVALID;
     for (int i = 0; i < n_ctx; i++)
-        if (!ctxs[i] || !ctxs[i]->d_slots || ctxs[i]->cfg.key_mode != ctxs[0]->cfg.key_mode) return FA_ERR_INVALID;
+        if (!ctxs[i] || !ctxs[i]->d_slots || ctxs[i]->cfg.key_mode != ctxs[0]->cfg.key_mode || ctxs[i]->flush_pending) return FA_ERR_INVALID;
     if (n_ctx == 1) return fa_flush(ctxs[0], rows, cap, n, flags);
     // 1. every context: fold the replicas, compact its rows (unsorted) into its scratch block, empty its table
     std::vector<uint64_t> groups(n_ctx, 0);
@@ -1067,12 +1289,12 @@ extern "C" int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t
         if (rc) return rc;
         rc = read_counters(c);
         if (rc) return rc;
-        groups[i] = c->h_counters->n_groups;
-        dropped += c->h_counters->n_dropped;
+        groups[i] = c->h_ts->n_groups;
+        dropped += c->h_ts->n_dropped;
         if (groups[i]) {
             rc = ensure_scratch(c, groups[i] * sizeof(fa_row));
             if (rc) return rc;
-            FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+            FA_CUDA(c, cudaMemsetAsync(&c->d_ts->flush_rows, 0, 8, c->stream));
             cudaError_t e;
 #define CALL_COMPACT(K) launch_compact<K>(c, (fa_row *)c->d_scratch, groups[i])
             FA_DISPATCH_KW(c->kw, CALL_COMPACT)
@@ -1099,8 +1321,8 @@ extern "C" int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t
         FA_CUDA(c, cudaSetDevice(c->cfg.device));
         int rc = read_counters(c);
         if (rc) return rc;
-        total += c->h_counters->n_groups;
-        dropped += c->h_counters->n_dropped;
+        total += c->h_ts->n_groups;
+        dropped += c->h_ts->n_dropped;
     }
     *n = (size_t)total;
     if (total > cap || (total && !rows)) return FA_ERR_CAPACITY;
@@ -1126,6 +1348,7 @@ extern "C" int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t
 
 extern "C" int fa_reset(fa_ctx *c)
 {
+    if (c && c->flush_pending) return FA_ERR_INVALID;  // fa_flush_end first
     if (!c) return FA_ERR_INVALID;
     int rc = fa_sync(c);
     if (rc) return rc;
@@ -1133,6 +1356,7 @@ extern "C" int fa_reset(fa_ctx *c)
     if (rc) return rc;
     if (c->d_cms) FA_CUDA(c, cudaMemsetAsync(c->d_cms, 0, c->cms_words * 8, c->stream));
     FA_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    FA_CUDA(c, cudaMemsetAsync(c->d_ts, 0, sizeof(TableState), c->stream));
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[1][0], 1, 8, c->stream));
     c->n_records = c->n_submits = c->bytes_in = 0;
     c->n_kernels = 0;
@@ -1209,6 +1433,7 @@ __global__ void k_hh_gather(const fa_hh *hh, const uint32_t *idx, uint32_t m, fa
 
 extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t *n)
 {
+    if (c && c->flush_pending) return FA_ERR_INVALID;  // fa_flush_end first
     if (!c || !n || !c->d_cms || !c->d_slots || (k && !out)) return FA_ERR_INVALID;
     int rc = fa_sync(c);
     if (rc) return rc;
@@ -1216,7 +1441,7 @@ extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t 
     if (rc) return rc;
     rc = read_counters(c);
     if (rc) return rc;
-    const uint64_t groups = c->h_counters->n_groups;
+    const uint64_t groups = c->h_ts->n_groups;
     *n = 0;
     if (!groups || !k) return FA_OK;
     if (groups >= (1ull << 31)) return FA_ERR_INVALID;
@@ -1243,7 +1468,7 @@ extern "C" int fa_topk_local(fa_ctx *c, int which, size_t k, fa_hh *out, size_t 
     uint32_t *idx_a = (uint32_t *)(base + hh_b + 2 * k_b), *idx_b = (uint32_t *)(base + hh_b + 2 * k_b + i_b);
     fa_hh *d_head = (fa_hh *)(base + hh_b + 2 * k_b + 2 * i_b);
     void *cub_tmp = base + hh_b + 2 * k_b + 2 * i_b + head_b;
-    FA_CUDA(c, cudaMemsetAsync(&c->d_counters->flush_rows, 0, 8, c->stream));
+    FA_CUDA(c, cudaMemsetAsync(&c->d_ts->flush_rows, 0, 8, c->stream));
     cudaError_t e;
 #define CALL_EST(K) launch_estimate<K>(c, cms, d_hh, groups)
     FA_DISPATCH_KW(c->kw, CALL_EST)

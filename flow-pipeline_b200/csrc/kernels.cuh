@@ -33,9 +33,14 @@ constexpr uint32_t kHotReplicas = 64;  // CTA b uses replica b mod 64
 constexpr uint32_t kHotSlots = 1024;   // slots per replica (power of two)
 constexpr uint32_t kHotProbes = 8;     // bounded probe sequence; a miss falls through to the main table
 
-struct Counters {
-    unsigned long long n_bad, n_nokey, n_dropped, n_groups, flush_rows;
+// per group table (a context has two: the one being filled and the one being flushed)
+struct TableState {
+    unsigned long long n_groups, n_dropped, flush_rows;
     unsigned int side_state, pad0;
+};
+
+struct Counters {
+    unsigned long long n_bad, n_nokey;
     // key-repetition statistics of the two most recent submits: {lanes whose key repeats inside their warp,
     // lanes looked at}, sampled from every 64th tile.  Submit i decides from what submit i-1 saw.
     unsigned int hint[2][2];
@@ -59,6 +64,7 @@ struct SubmitParams {
     unsigned long long *cms;
     uint32_t cms_depth, cms_wlog2;
     Counters *counters;
+    TableState *tstate;  // of the table behind `slots`
     uint32_t hint_set;  // this submit writes counters->hint[hint_set], reads hint[hint_set ^ 1]
     // hot-key replicas: kHotReplicas small tables of kHotSlots slots (same slot layout as the main table)
     uint8_t *hot_slots;
@@ -215,7 +221,7 @@ __device__ __forceinline__ void side_slot_add(const SubmitParams &p, unsigned lo
                                               unsigned long long count)
 {
     uint8_t *s = p.slots + ((size_t)p.slot_mask + 1) * SlotLayout<KW>::BYTES;
-    if (atomicCAS(&p.counters->side_state, 0u, 1u) == 0u) atomicAdd(&p.counters->n_groups, 1ull);
+    if (atomicCAS(&p.tstate->side_state, 0u, 1u) == 0u) atomicAdd(&p.tstate->n_groups, 1ull);
     slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
 }
 
@@ -234,7 +240,7 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
             if (cur == ~0ull) {
                 cur = atomicCAS(reinterpret_cast<unsigned long long *>(s), ~0ull, k);
                 if (cur == ~0ull) {
-                    atomicAdd(&p.counters->n_groups, 1ull);
+                    atomicAdd(&p.tstate->n_groups, 1ull);
                     cur = k;
                 }
             }
@@ -253,7 +259,7 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
             if ((clo & chi) == ~0ull) {
                 cas_u128(s, ~0ull, ~0ull, klo, khi, clo, chi);
                 if ((clo & chi) == ~0ull) {
-                    atomicAdd(&p.counters->n_groups, 1ull);
+                    atomicAdd(&p.tstate->n_groups, 1ull);
                     clo = klo;
                     chi = khi;
                 }
@@ -277,7 +283,7 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
 #pragma unroll
                     for (int i = 0; i < KW; i++) skey[i] = key[i];
                     st_release_u32(state, SLOT_READY);
-                    atomicAdd(&p.counters->n_groups, 1ull);
+                    atomicAdd(&p.tstate->n_groups, 1ull);
                     return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
                 }
                 st = old;
@@ -294,7 +300,7 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
             slot = (slot + 1) & p.slot_mask;
         }
     }
-    atomicAdd(&p.counters->n_dropped, count);
+    atomicAdd(&p.tstate->n_dropped, count);
 }
 
 // Bounded insert into one hot-key replica (KW <= 4 layouts only).  Returns false when the probe
@@ -788,7 +794,7 @@ __device__ __forceinline__ bool slot_read(const uint8_t *s, bool is_side, bool s
 
 template <int KW>
 __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsigned long long n_slots, fa_row *rows,
-                                                      unsigned long long cap, Counters *counters)
+                                                      unsigned long long cap, TableState *counters)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
@@ -836,7 +842,7 @@ __global__ void __launch_bounds__(256) k_add_rows(const SubmitParams p, const fa
 template <int KW>
 __global__ void __launch_bounds__(256) k_estimate(const uint8_t *slots, unsigned long long n_slots, const unsigned long long *cms,
                                                   uint32_t depth, uint32_t wlog2, fa_hh *out, unsigned long long cap,
-                                                  Counters *counters)
+                                                  TableState *counters)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;

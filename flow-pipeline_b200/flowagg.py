@@ -96,6 +96,8 @@ _PROTOS = {
     "fa_sync": (C.c_int, [C.c_void_p]),
     "fa_stats_get": (C.c_int, [C.c_void_p, C.POINTER(FaStats)]),
     "fa_flush": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32]),
+    "fa_flush_begin": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "fa_flush_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fa_merge_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32]),
     "fa_row_owner": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
     "fa_flush_box": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32]),
@@ -269,6 +271,28 @@ class FlowAgg:
                 out = None
                 continue
             self._check(rc, "fa_flush", ok)
+            self._rows_cap = max(len(rows), 1 << 16)
+            return rows[: n.value]
+
+    def flush_begin(self, keep=False, sort=True):
+        """First half of an asynchronous flush: swap tables and enqueue the drain on the side stream; returns at once.
+        Submits issued from now on already fill the fresh table."""
+        flags = (FA_FLUSH_KEEP if keep else 0) | (0 if sort else FA_FLUSH_UNSORTED)
+        self._check(self._L.fa_flush_begin(self._h, flags), "fa_flush_begin")
+
+    def flush_end(self, allow_full=False, out=None):
+        """Second half: wait for the drain (blocking, not spinning) and return the rows (same conventions as flush)."""
+        ok = (0, -5) if allow_full else (0,)
+        n = C.c_size_t()
+        cap = len(out) if out is not None else getattr(self, "_rows_cap", 1 << 16)
+        while True:
+            rows = out if out is not None and len(out) >= cap else np.empty(cap, dtype=ROW_DTYPE)
+            rc = self._L.fa_flush_end(self._h, rows.ctypes.data, len(rows), C.byref(n))
+            if rc == -4 and n.value > len(rows):  # FA_ERR_CAPACITY: the rows are kept, retry with the size it reported
+                cap = n.value
+                out = None
+                continue
+            self._check(rc, "fa_flush_end", ok)
             self._rows_cap = max(len(rows), 1 << 16)
             return rows[: n.value]
 

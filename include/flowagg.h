@@ -176,6 +176,18 @@ int fa_stats_get(fa_ctx *ctx, fa_stats *out); /* implies fa_sync */
  * cap < *n (nothing is reset then). */
 int fa_flush(fa_ctx *ctx, fa_row *rows, size_t cap, size_t *n, uint32_t flags);
 
+/* The same flush in two halves, so that it never stalls the stream ((*state).flush holds the inserter's global mutex
+ * while it talks to the database, inserter.go:90-111, and buffer() waits behind it; here the next submit does not):
+ * fa_flush_begin folds the hot-key replicas, swaps the filled group table for a spare, empty one -- every later
+ * fa_submit already aggregates into the spare -- and enqueues compaction, ORDER BY, the copies to pinned host memory and
+ * the emptying of the old table on a side stream; it returns at once.  fa_flush_end waits for that work (the thread
+ * sleeps on a blocking event, it does not spin) and copies the rows out; same results and errors as fa_flush (with
+ * FA_ERR_CAPACITY the rows are kept: call fa_flush_end again with a larger array).  One flush in flight per context;
+ * between the two halves only fa_submit*, fa_sync, fa_stats_get and fa_host_buffer may be called on it.  Group tables
+ * of more than 2^22 slots, FA_FLUSH_KEEP and FA_FLUSH_UNSORTED are drained by fa_flush_end itself (no spare table). */
+int fa_flush_begin(fa_ctx *ctx, uint32_t flags);
+int fa_flush_end(fa_ctx *ctx, fa_row *rows, size_t cap, size_t *n);
+
 /* The merge step of the SummingMergeTree behind flows_5m (compose/clickhouse/create.sh:88-90: rows with equal
  * ORDER BY keys are summed) for rows that are already aggregates -- an earlier window's or another context's
  * fa_flush output.  `rows` may be host or device memory (a peer GPU's included).  n_owners > 1 adds only the rows

@@ -891,3 +891,46 @@ def test_rollup_boundary_vectors_on_the_gpu(fp, oracle, torch_cuda, rollup_bound
                 got = [(tuple(int(x) for x in r["key"][:4]), int(r["bytes"]), int(r["packets"]), int(r["count"])) for r in rows]
                 want = [(k, (2 * b) & (2 ** 64 - 1), (2 * p) & (2 ** 64 - 1), 2 * c) for k, b, p, c in rollup_case_rows(case)]
                 assert got == want, (case["name"], framed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["aspair", "flows5m", "srcaddr", "5tuple", "dstport"])
+def test_asynchronous_flush_equals_the_synchronous_one(fp, oracle, torch_cuda, mode):
+    """fa_flush_begin / fa_flush_end: the filled table is swapped for a spare and drained on a side stream while the next
+    submits already aggregate into the spare.  Window by window the rows equal the oracle's (and fa_flush's), whatever is
+    submitted between the two halves; row-count guesses that are too small, caller arrays that are too small, peeks and
+    unsorted dumps included."""
+    cfg = fp.FaMockerConfig.make(seed=5, flows_per_second=50, n_src_as=40, n_dst_as=40, framed=True, addr_mode=fp.FA_ADDR_ZIPF24 if mode == "srcaddr" else 0)
+    windows = [fp.mocker_host(cfg, i * 30000, n) for i, n in enumerate((30000, 500, 30000, 30000, 7))]
+    want = [oracle.run_batch(b, o, key_mode=mode)[0] for b, o in windows]
+    with fp.FlowAgg(mode, device=0, table_capacity=1 << 17) as a:
+        a.submit(*windows[0], framed=True)
+        a.flush_begin()
+        a.submit(*windows[1], framed=True)              # lands in the spare table while window 0 drains
+        st = a.stats()                                  # allowed between the halves: counts the CURRENT table
+        assert st["n_groups"] == len(want[1])
+        assert np.array_equal(a.flush_end(), want[0])
+        a.flush_begin()                                 # window 1 is tiny: the next guess (its row count + 1/8) is far too small ...
+        a.submit(*windows[2], framed=True)
+        assert np.array_equal(a.flush_end(), want[1])
+        a.flush_begin()                                 # ... for window 2: the exact path re-sorts from scratch
+        a.submit(*windows[3], framed=True)
+        small = np.empty(3, dtype=fp.ROW_DTYPE)         # a caller array that is too small: rows are kept, the call repeats
+        assert np.array_equal(a.flush_end(out=small), want[2])
+        assert np.array_equal(a.flush(), want[3])       # the synchronous flush on the swapped-in table
+        a.submit(*windows[4], framed=True)
+        a.flush_begin(keep=True)                        # a peek: drained in place by flush_end
+        assert np.array_equal(a.flush_end(), want[4])
+        a.flush_begin(sort=False)
+        rows = a.flush_end()
+        assert np.array_equal(rows[np.lexsort([rows["key"][:, k] for k in range(11, -1, -1)])], want[4])
+        assert len(a.flush()) == 0
+    # one flush in flight: a second begin, a plain flush or a box query in between is refused, not queued
+    with fp.FlowAgg(mode, device=0, table_capacity=1 << 17) as a:
+        a.submit(*windows[0], framed=True)
+        a.flush_begin()
+        with pytest.raises(fp.FlowAggError):
+            a.flush_begin()
+        with pytest.raises(fp.FlowAggError):
+            a.flush()
+        assert np.array_equal(a.flush_end(), want[0])
