@@ -266,16 +266,9 @@ def box_check(fp, torch, dist, dev, local_rank, rank, world, stream, slabs, n_fl
         torch.cuda.synchronize()
         return r, dmax(e0.elapsed_time(e1))
 
-    # ---- 1a. exact roll-up of the full windows
+    # ---- 1a. against the oracle, on a slice the CPU can do (also warms up NCCL's all-to-all before anything is timed)
     agg = fp.FlowAgg("aspair", device=local_rank, stream=stream, table_capacity=TABLE_CAP)
-    for (d_buf, d_off, n, nb) in slabs:
-        agg.submit_device(d_buf, d_off, n, nb)
-    share, ms = timed(lambda: par.exchange_rows(agg, device=dev))
-    out["box_flush_ms"] = ms
-    owners = fp.row_owner("aspair", share, world)
-    ok = bool((owners == rank).all()) and dsum(len(share)) == 65536 and dsum(int(share["count"].sum())) == world * n_flows
-    out["box_rollup_groups"] = dsum(len(share))
-    # ---- 1b. the same against the oracle, on a slice the CPU can do
+    ok = True
     m = min(1 << 21, n_flows)
     cfg = mocker_cfg(fp, partition)
     d_buf = torch.empty(m * 88 + 4096, dtype=torch.uint8, device=dev)
@@ -290,8 +283,17 @@ def box_check(fp, torch, dist, dev, local_rank, rank, world, stream, slabs, n_fl
         parts = [o.mocker_host(seed=1 + (partition - rank + r), first=0, n=m, **MOCKER) for r in range(world)]
         want, _ = o.run_slabs(parts, framed=True, key_mode="aspair", threads=usable_cores())
         want = want[fp.row_owner("aspair", want, world) == 0]
-        ok = ok and bool(np.array_equal(share, want))
+        ok = bool(np.array_equal(share, want))
         out["box_rollup_oracle_slice"] = f"{world} x {m} flows: rank 0's share ({len(share)} rows) == oracle rows it owns"
+    # ---- 1b. exact roll-up of the full windows, timed
+    for (d_buf, d_off, n, nb) in slabs:
+        agg.submit_device(d_buf, d_off, n, nb)
+    share, ms = timed(lambda: par.exchange_rows(agg, device=dev))
+    out["box_flush_ms"] = ms
+    owners = fp.row_owner("aspair", share, world)
+    n_groups_box, n_count_box = dsum(len(share)), dsum(int(share["count"].sum()))  # collectives: every rank, unconditionally
+    ok = ok and bool((owners == rank).all()) and n_groups_box == 65536 and n_count_box == world * n_flows
+    out["box_rollup_groups"] = n_groups_box
     agg.close()
     out["box_rollup"] = "ok" if dsum(0 if ok else 1) == 0 else "MISMATCH"
 
