@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--box-check", action="store_true", help=argparse.SUPPRESS)  # run the box-wide queries at N=1 too
+    ap.add_argument("--no-frame-leg", action="store_true", help=argparse.SUPPRESS)  # skip the offsets-free (framed stream) timing
     ap.add_argument("--partition", type=int, default=None, help=argparse.SUPPRESS)  # which producer instance (default: rank)
     ap.add_argument("--first", type=int, default=0, help=argparse.SUPPRESS)  # first SequenceNum (>= 2^28: 5-byte varints, 86-byte records)
     args = ap.parse_args()
@@ -490,6 +491,29 @@ def main():
     kernel_gbs = sum(k_bytes) / (sum(k_ms) * 1e-3) / 1e9
     peak, peak_src = measured_peak()
 
+    # ---- the same window WITHOUT host-supplied offsets (the Clickhouse Kafka-engine framing, create.sh:28-34): the library
+    # finds the record boundaries on the GPU (csrc/frame.cuh) before the fused kernel.  Reported beside the headline, not as it.
+    framed_stream = None
+    if not args.no_frame_leg:
+        fagg = fp.FlowAgg("aspair", device=local_rank, stream=stream, table_capacity=TABLE_CAP)
+        for (d_buf, d_off, n, nb) in slabs:          # warm-up pass (allocates the index scratch)
+            fagg.submit_device(d_buf, None, 0, nb)
+        frows = fagg.flush()
+        assert np.array_equal(frows, rows), "offsets found on the GPU give other rows"
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for (d_buf, d_off, n, nb) in slabs:
+            fagg.submit_device(d_buf, None, 0, nb)
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1)
+        fagg.flush()
+        fagg.close()
+        framed_stream = {"value": n_flows / (fms * 1e-3), "unit": "flows/s", "ms_per_slab": fms / len(slabs),
+                         "with_offsets_ms_per_slab": sum(k_ms) / len(k_ms),
+                         "note": "fa_submit_device(offsets = NULL): speculate / walk / verify / scan / emit on the GPU, then the same fused kernel"}
+
     # ---- e2e: pinned host buffers through fa_submit, rows read back ----
     e2e = None
     if not args.no_e2e:
@@ -588,6 +612,7 @@ def main():
                          "algorithmic_bytes_per_flow": alg_bytes / n_flows, "avg_launch_ms": sum(k_ms) / len(k_ms),
                          "launches_timed": len(k_ms), "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "framed_stream": framed_stream,
         }
         if box is not None:
             out.update(box)

@@ -40,6 +40,7 @@ struct fa_ctx {
     uint32_t slot_bytes = 0;
     uint64_t capacity = 0;
     bool weighted = false;
+    uint32_t admit_shift = 0;  // FA_CFG_TOPK_ONLY: log2(64 * topk_k), 0 otherwise
 
     cudaStream_t stream = nullptr;  // compute
     cudaStream_t copy_stream = nullptr;
@@ -317,6 +318,21 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     c->kw = k_key_words[c->cfg.key_mode];
     c->slot_bytes = slot_bytes_for(c->kw);
     c->weighted = (c->cfg.flags & (FA_CFG_CMS | FA_CFG_SCALE_SAMPLING)) != 0;
+    if (c->cfg.flags & FA_CFG_TOPK_ONLY) {
+        // heavy hitters only: a sketch plus a bounded candidate table, address keys (KW == 4)
+        if (!(c->cfg.flags & FA_CFG_CMS) || c->kw != 4 || (c->cfg.flags & (FA_CFG_NO_AGGREGATE | FA_CFG_SCALE_SAMPLING))) return FA_ERR_INVALID;
+        const uint64_t k = c->cfg.topk_k ? c->cfg.topk_k : 1000;
+        uint32_t shift = 6;  // 64 x K candidates can truly weigh more than total / (64 K)
+        while ((1ull << (shift - 6)) < k) shift++;
+        c->admit_shift = shift;
+        const uint64_t want = 4ull << shift;
+        if (cfg->table_capacity == 0) {
+            c->capacity = want;
+        } else if (c->capacity < want) {
+            c->last_error = "FA_CFG_TOPK_ONLY needs table_capacity >= 256 * topk_k";
+            return FA_ERR_INVALID;
+        }
+    }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -483,6 +499,7 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.cms = c->d_cms;
     p.cms_depth = c->cfg.cms_depth;
     p.cms_wlog2 = c->cfg.cms_width_log2;
+    p.admit_shift = c->admit_shift;
     p.hint_set = (uint32_t)(c->n_submits & 1u);
     if (c->d_hot) c->hot_dirty = true;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[p.hint_set][0], 0, 8, c->stream));  // this submit's statistics start at zero
@@ -526,6 +543,32 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
 #undef CALL_FUSED
     }
     FA_CUDA(c, e);
+    if (c->admit_shift && c->d_slots) {
+        // FA_CFG_TOPK_ONLY: publish the total weight, keep only the candidates still above the bar (kernels.cuh: k_prune_*)
+        const unsigned long long n_slots = c->capacity + 1;
+        int rc = ensure_scratch(c, n_slots * sizeof(fa_row));
+        if (rc) return rc;
+        const int g = (int)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)c->num_sms * 8);
+        // the heavy keys' updates sit in the replicas and their sketch weight in the slots: settle both first
+        k_merge_hot_candidates<<<c->num_sms, 256, 0, c->stream>>>(p, kHotReplicas * kHotSlots);
+        k_apply_pending<<<g, 256, 0, c->stream>>>(p, c->capacity);
+        c->n_kernels += 2;
+        c->hot_dirty = false;
+        k_publish_weight<<<1, 1, 0, c->stream>>>(c->d_counters, c->d_ts);
+        k_prune_collect<<<g, 256, 0, c->stream>>>(c->d_slots, n_slots, c->d_cms, c->cfg.cms_depth, c->cfg.cms_width_log2, c->admit_shift,
+                                                   c->d_counters, (fa_row *)c->d_scratch, c->d_ts);
+        c->n_kernels += 2;
+        FA_CUDA(c, cudaGetLastError());
+        rc = table_init_at(c, c->d_slots, c->stream, false);
+        if (rc) return rc;
+        FA_CUDA(c, cudaMemsetAsync(&c->d_ts->n_groups, 0, 8, c->stream));
+        FA_CUDA(c, cudaMemsetAsync(&c->d_ts->side_state, 0, 4, c->stream));
+        SubmitParams pp{};
+        fill_table_params(c, pp);
+        k_prune_reinsert<<<g, 256, 0, c->stream>>>(pp, (const fa_row *)c->d_scratch);
+        c->n_kernels++;
+        FA_CUDA(c, cudaGetLastError());
+    }
     FA_CUDA(c, cudaEventRecord(busy[1], c->stream));
     c->busy_head++;
     c->n_submits++;

@@ -41,6 +41,9 @@ struct TableState {
 
 struct Counters {
     unsigned long long n_bad, n_nokey;
+    // FA_CFG_TOPK_ONLY: sum of the sketched weights.  total_weight is what the admission threshold of the RUNNING launch scales
+    // with (stable while it runs); the launch adds its own weights to total_weight_acc, which k_prune_* publishes afterwards.
+    unsigned long long total_weight, total_weight_acc;
     // key-repetition statistics of the two most recent submits: {lanes whose key repeats inside their warp,
     // lanes looked at}, sampled from every 64th tile.  Submit i decides from what submit i-1 saw.
     unsigned int hint[2][2];
@@ -63,6 +66,8 @@ struct SubmitParams {
     // sketch (nullptr = off)
     unsigned long long *cms;
     uint32_t cms_depth, cms_wlog2;
+    uint32_t admit_shift;  // FA_CFG_TOPK_ONLY: a key enters the (bounded) candidate table only once its sketch estimate
+                           // reaches total_weight >> admit_shift; 0 = every key is a candidate (the exact group table)
     Counters *counters;
     TableState *tstate;  // of the table behind `slots`
     uint32_t hint_set;  // this submit writes counters->hint[hint_set], reads hint[hint_set ^ 1]
@@ -265,12 +270,22 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
                 }
             }
             if (clo == klo && chi == khi) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+            // PTX does not promise that a 16-byte vector load is one atomic access: a snapshot that LOOKS half written (one
+            // half ours, or one half still all ones) is re-read through the CAS unit, whose answer is atomic, before the probe
+            // moves on -- a torn read must never send a key to a second slot
+            if (clo == klo || chi == khi || clo == ~0ull || chi == ~0ull) {
+                cas_u128(s, ~0ull, ~0ull, klo, khi, clo, chi);
+                if ((clo & chi) == ~0ull) {  // it was empty after all and is ours now
+                    atomicAdd(&p.tstate->n_groups, 1ull);
+                    clo = klo;
+                    chi = khi;
+                }
+                if (clo == klo && chi == khi) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
+            }
             slot = (slot + 1) & p.slot_mask;
         }
     } else {
-        // wide keys (5-tuple): EMPTY -> BUSY (CAS) -> key written -> READY (release).  A reader
-        // that sees READY through a relaxed load re-reads with acquire only when it has to
-        // decide a MISmatch on a key it may have read before it was published.
+        // wide keys (5-tuple): EMPTY -> BUSY (CAS) -> key written -> READY (release)
 #pragma unroll 1
         for (uint32_t probe = 0; probe <= p.slot_mask; probe++) {
             uint8_t *s = p.slots + (size_t)slot * SlotLayout<KW>::BYTES;
@@ -292,10 +307,18 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
                 __nanosleep(32);
                 st = ld_acquire_u32(state);
             }
-            // state READY was observed before these loads are issued (dependent branch above)
+            // READY may have been seen through a relaxed load: the key words read next are then not ordered behind the
+            // publisher's stores by the memory model.  A match needs no more (the words equal ours, whoever wrote them); a
+            // MISmatch is only believed after the state has been re-read with acquire and the key compared again.
             bool same = true;
 #pragma unroll
             for (int i = 0; i < KW; i++) same &= (ld_relaxed_u32(skey + i) == key[i]);
+            if (!same) {
+                while (ld_acquire_u32(state) != SLOT_READY) __nanosleep(32);
+                same = true;
+#pragma unroll
+                for (int i = 0; i < KW; i++) same &= (ld_relaxed_u32(skey + i) == key[i]);
+            }
             if (same) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
             slot = (slot + 1) & p.slot_mask;
         }
@@ -365,11 +388,116 @@ __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long lon
     }
 }
 
+__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old;
+    asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+
+// the same update, returning the key's estimate right after it (min over the rows of the counters just written)
+__device__ __forceinline__ unsigned long long cms_add_estimate(const SubmitParams &p, unsigned long long h, unsigned long long weight)
+{
+    const uint32_t a = (uint32_t)h, b = (uint32_t)(h >> 32) | 1u;
+    const uint32_t mask = (1u << p.cms_wlog2) - 1u;
+    unsigned long long est = ~0ull;
+    for (uint32_t j = 0; j < p.cms_depth; j++) {
+        const uint32_t idx = (a + j * b) & mask;
+        const unsigned long long now = atom_add_u64(p.cms + ((size_t)j << p.cms_wlog2) + idx, weight) + weight;
+        est = now < est ? now : est;
+    }
+    return est;
+}
+
+// Bounded insert into the candidate table of FA_CFG_TOPK_ONLY: at most kCandProbes slots are looked at; a key that finds
+// neither itself nor a free slot is simply not a candidate (yet: its next flow tries again, and the table is pruned after
+// every submit).  KW == 4 layout (addresses).
+constexpr uint32_t kCandProbes = 16;
+__device__ __forceinline__ void candidate_add(const SubmitParams &p, const uint32_t *key, unsigned long long h, unsigned long long bytes,
+                                              unsigned long long packets, unsigned long long count)
+{
+    const unsigned long long klo = (unsigned long long)key[0] | ((unsigned long long)key[1] << 32);
+    const unsigned long long khi = (unsigned long long)key[2] | ((unsigned long long)key[3] << 32);
+    if ((klo & khi) == ~0ull) return side_slot_add<4>(p, bytes, packets, count);
+    uint32_t slot = (uint32_t)(h >> 32) & p.slot_mask;
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < kCandProbes; probe++) {
+        uint8_t *s = p.slots + (size_t)slot * SlotLayout<4>::BYTES;
+        unsigned long long clo, chi;
+        ld_relaxed_u128(s, clo, chi);
+        if ((clo & chi) == ~0ull) {
+            cas_u128(s, ~0ull, ~0ull, klo, khi, clo, chi);
+            if ((clo & chi) == ~0ull) {
+                atomicAdd(&p.tstate->n_groups, 1ull);
+                clo = klo;
+                chi = khi;
+            }
+        }
+        if (clo == klo && chi == khi) return slot_add(s + SlotLayout<4>::VAL_OFF, bytes, packets, count);
+        slot = (slot + 1) & p.slot_mask;
+    }
+}
+
+// the key's slot in the candidate table, or nullptr (bounded probe; an empty slot ends the search)
+__device__ __forceinline__ uint8_t *candidate_find(const SubmitParams &p, unsigned long long klo, unsigned long long khi, unsigned long long h)
+{
+    uint32_t slot = (uint32_t)(h >> 32) & p.slot_mask;
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < kCandProbes; probe++) {
+        uint8_t *s = p.slots + (size_t)slot * SlotLayout<4>::BYTES;
+        unsigned long long clo, chi;
+        ld_relaxed_u128(s, clo, chi);
+        if (clo == klo && chi == khi) return s;
+        if ((clo & chi) == ~0ull) return nullptr;
+        slot = (slot + 1) & p.slot_mask;
+    }
+    return nullptr;
+}
+
+// A candidate's flow: its sums AND its sketch weight go to the slot (the 48-byte slot's spare word holds the weight not yet
+// in the sketch); k_apply_pending moves the weight into the sketch after the launch.  One hot address per heavy key would
+// serialise in L2 exactly like the hot groups of a roll-up, so the CTA's replica takes the update when it can.
+__device__ __forceinline__ void slot_add_pending(uint8_t *s, unsigned long long bytes, unsigned long long packets, unsigned long long count,
+                                                 unsigned long long weight)
+{
+    unsigned long long *v = reinterpret_cast<unsigned long long *>(s + SlotLayout<4>::VAL_OFF);
+    red_add_u64(v + 0, bytes);
+    red_add_u64(v + 1, packets);
+    red_add_u64(v + 2, count);
+    red_add_u64(v + 3, weight);
+}
+
+__device__ __forceinline__ bool hot_add_pending(uint8_t *replica, unsigned long long klo, unsigned long long khi, unsigned long long h,
+                                                unsigned long long bytes, unsigned long long packets, unsigned long long weight)
+{
+    uint32_t slot = (uint32_t)(h >> 20) & (kHotSlots - 1u);
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < kHotProbes; probe++) {
+        uint8_t *s = replica + (size_t)slot * SlotLayout<4>::BYTES;
+        unsigned long long clo, chi;
+        ld_relaxed_u128(s, clo, chi);
+        if ((clo & chi) == ~0ull) {
+            cas_u128(s, ~0ull, ~0ull, klo, khi, clo, chi);
+            if ((clo & chi) == ~0ull) {
+                clo = klo;
+                chi = khi;
+            }
+        }
+        if (clo == klo && chi == khi) {
+            slot_add_pending(s, bytes, packets, 1ull, weight);
+            return true;
+        }
+        slot = (slot + 1) & (kHotSlots - 1u);
+    }
+    return false;
+}
+
 // One decoded flow into the group table (+ sketch).  hot: this submit sends updates through the CTA's
 // replica first (keys repeat a lot: one shared slot per key would serialise in L2).
 // Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
 template <int MODE>
-__device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have)
+__device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have,
+                                                   unsigned long long &total_w)
 {
     constexpr int KW = KeyTraits<MODE>::KW;
     uint32_t key[KW];
@@ -383,6 +511,27 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
     if (p.scale) {  // sum(Bytes*SamplingRate): viz-ch.json:74
         b *= f.sampling_rate;
         pk *= f.sampling_rate;
+    }
+    if (KW == 4 && p.cms && p.admit_shift) {
+        // heavy hitters only (viz-ch.json:233's top-N): the sketch sees every flow, the candidate table only keys whose estimate
+        // has reached the admission threshold -- memory is bounded by 2^admit_shift candidates, whatever the number of keys
+        const unsigned long long w = f.bytes * f.sampling_rate;
+        const unsigned long long klo = (unsigned long long)key[0] | ((unsigned long long)key[KW == 4 ? 1 : 0] << 32);
+        const unsigned long long khi = (unsigned long long)key[KW == 4 ? 2 : 0] | ((unsigned long long)key[KW == 4 ? 3 : 0] << 32);
+        uint8_t *cs = (p.slots && (klo & khi) != ~0ull) ? candidate_find(p, klo, khi, h) : nullptr;
+        if (cs) {
+            // already a candidate (a heavy key): slot and sketch weight through the CTA's replica; the sketch is settled after the launch
+            bool done = false;
+            if (p.hot_slots)
+                done = hot_add_pending(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<4>::BYTES, klo, khi, h, b, pk, w);
+            if (!done) slot_add_pending(cs, b, pk, 1ull, w);
+        } else {
+            const unsigned long long est = cms_add_estimate(p, h, w);
+            const unsigned long long seen = __ldg(&p.counters->total_weight);  // as of this launch's start (nothing writes it meanwhile)
+            if (p.slots && est >= (seen >> p.admit_shift)) candidate_add(p, key, h, b, pk, 1ull);
+        }
+        total_w += w;
+        return (uint32_t)h;
     }
     if (p.slots) {
         bool done = false;
@@ -505,11 +654,26 @@ struct AggConsumer {
     struct Item {
         uint32_t h32;
         bool have;
+        unsigned long long weight;  // sketched weight of the record (FA_CFG_TOPK_ONLY keeps the running total)
     };
     static __device__ __forceinline__ void item_clear(Item &it)
     {
         it.h32 = 0;
         it.have = false;
+        it.weight = 0;
+    }
+    static __device__ __forceinline__ void add_weight_one(const SubmitParams &p, const Item &it)  // a record parsed out of line
+    {
+        if (KW == 4 && WEIGHTED && p.admit_shift && it.weight) atomicAdd(&p.counters->total_weight_acc, it.weight);
+    }
+    // the tile's sketched weight into the context's running total (one atomic per warp)
+    static __device__ __forceinline__ void add_weight(const SubmitParams &p, const Item &it)
+    {
+        if (KW != 4 || !WEIGHTED || !p.admit_shift) return;
+        unsigned long long w = it.weight;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, d);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&p.counters->total_weight_acc, w);
     }
     static __device__ __forceinline__ bool want_hot(const SubmitParams &p)
     {
@@ -522,7 +686,7 @@ struct AggConsumer {
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have);
+            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have, it.weight);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
@@ -557,6 +721,8 @@ struct ColConsumer {
     static __device__ __forceinline__ void item_clear(Item &) {}
     static __device__ __forceinline__ bool want_hot(const SubmitParams &) { return false; }
     static __device__ __forceinline__ void sample_repeats(const SubmitParams &, const Item &) {}
+    static __device__ __forceinline__ void add_weight(const SubmitParams &, const Item &) {}
+    static __device__ __forceinline__ void add_weight_one(const SubmitParams &, const Item &) {}
     static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool, Item &)
     {
         consume(tp, r, ok, f, bad, nokey);
@@ -617,6 +783,7 @@ __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32
     typename Consumer::Item it;
     Consumer::item_clear(it);
     Consumer::consume(tp, r, ok, f, bad, nokey, false, it);
+    Consumer::add_weight_one(tp.p, it);
     return bad | (nokey << 1);
 }
 
@@ -682,6 +849,7 @@ __global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / T
         }
     }
     Consumer::sample_repeats(p, item);
+    Consumer::add_weight(p, item);
     flush_counts(p, bad, nokey);
 }
 
@@ -691,6 +859,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitParams p, const Columns c)
 {
     uint32_t nokey = 0;
+    unsigned long long wsum = 0;
     for (uint32_t r = blockIdx.x * kThreads + threadIdx.x; r < p.n_records; r += gridDim.x * kThreads) {
         if (!c.valid[r]) continue;
         Flow f;
@@ -719,8 +888,9 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
             f.dst_len = c.dst_addr_len[r] == 255 ? 17u : c.dst_addr_len[r];
         }
         bool have;
-        aggregate_flow<MODE>(p, f, nokey, false, have);
+        aggregate_flow<MODE>(p, f, nokey, false, have, wsum);
     }
+    if (wsum) atomicAdd(&p.counters->total_weight_acc, wsum);
     flush_counts(p, 0, nokey);
 }
 
@@ -814,6 +984,98 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsi
         r.packets = v[1];
         r.count = v[2];
         rows[at] = r;
+    }
+}
+
+// ---- FA_CFG_TOPK_ONLY: keep the candidate table small --------------------------------------------------------------
+//
+// After every submit: publish the running total of the sketched weights (the next launch's admission threshold scales
+// with it), then rebuild the candidate table from the candidates whose sketch estimate is still at or above the
+// threshold -- keys admitted early, when little had been seen and the bar was low, leave again.  Three launches over
+// <= table_capacity slots: collect survivors, empty the table, re-insert.
+// fold the replicas' candidate updates (sums + pending sketch weight) into the main candidate table, empty the replicas
+__global__ void __launch_bounds__(256) k_merge_hot_candidates(const SubmitParams p, uint32_t n_hot_slots)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hot_slots; i += gridDim.x * blockDim.x) {
+        uint8_t *s = p.hot_slots + (size_t)i * SlotLayout<4>::BYTES;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(s);
+        const unsigned long long klo = w[0], khi = w[1];
+        if ((klo & khi) == ~0ull) continue;
+        unsigned long long *v = reinterpret_cast<unsigned long long *>(s + SlotLayout<4>::VAL_OFF);
+        uint32_t key[4] = {(uint32_t)klo, (uint32_t)(klo >> 32), (uint32_t)khi, (uint32_t)(khi >> 32)};
+        const unsigned long long h = hash64<4>(key);
+        uint8_t *cs = candidate_find(p, klo, khi, h);
+        if (cs) {
+            slot_add_pending(cs, v[0], v[1], v[2], v[3]);
+        } else {  // left the table meanwhile (cannot happen within one launch, but never lose sketch weight)
+            cms_add(p, h, v[3]);
+            candidate_add(p, key, h, v[0], v[1], v[2]);
+        }
+        w[0] = w[1] = ~0ull;
+        v[0] = v[1] = v[2] = v[3] = 0ull;
+    }
+}
+
+// the candidates' weight that has not reached the sketch yet: add it now (the sketch is linear: when a weight lands does not matter)
+__global__ void __launch_bounds__(256) k_apply_pending(const SubmitParams p, unsigned long long n_slots)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint8_t *s = p.slots + i * SlotLayout<4>::BYTES;
+        const unsigned long long *k = reinterpret_cast<const unsigned long long *>(s);
+        if ((k[0] & k[1]) == ~0ull) continue;
+        unsigned long long *pend = reinterpret_cast<unsigned long long *>(s + SlotLayout<4>::VAL_OFF) + 3;
+        const unsigned long long w = *pend;
+        if (!w) continue;
+        *pend = 0ull;
+        uint32_t key[4] = {(uint32_t)k[0], (uint32_t)(k[0] >> 32), (uint32_t)k[1], (uint32_t)(k[1] >> 32)};
+        cms_add(p, hash64<4>(key), w);
+    }
+}
+
+__global__ void k_publish_weight(Counters *counters, TableState *ts)
+{
+    counters->total_weight = counters->total_weight_acc;
+    ts->flush_rows = 0;
+}
+
+__global__ void __launch_bounds__(256) k_prune_collect(const uint8_t *slots, unsigned long long n_slots, const unsigned long long *cms, uint32_t depth,
+                                                       uint32_t wlog2, uint32_t admit_shift, const Counters *counters, fa_row *rows, TableState *ts)
+{
+    const unsigned long long bar = counters->total_weight >> admit_shift;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t *s = slots + i * SlotLayout<4>::BYTES;
+        uint32_t key[4];
+        if (!slot_read<4>(s, i == n_slots - 1, ts->side_state != 0u, key)) continue;
+        if (i == n_slots - 1) key[0] = key[1] = key[2] = key[3] = 0xFFFFFFFFu;
+        const unsigned long long h = hash64<4>(key);
+        const uint32_t a = (uint32_t)h, b = (uint32_t)(h >> 32) | 1u, mask = (1u << wlog2) - 1u;
+        unsigned long long est = ~0ull;
+        for (uint32_t j = 0; j < depth; j++) {
+            const unsigned long long cnt = cms[((size_t)j << wlog2) + ((a + j * b) & mask)];
+            est = cnt < est ? cnt : est;
+        }
+        if (est < bar) continue;
+        const unsigned long long at = atomicAdd(&ts->flush_rows, 1ull);
+        fa_row r;
+#pragma unroll
+        for (int k = 0; k < FA_MAX_KEY_WORDS; k++) r.key[k] = k < 4 ? key[k] : 0u;
+        const unsigned long long *v = reinterpret_cast<const unsigned long long *>(s + SlotLayout<4>::VAL_OFF);
+        r.bytes = v[0];
+        r.packets = v[1];
+        r.count = v[2];
+        rows[at] = r;
+    }
+}
+
+// re-insert the ts->flush_rows survivors (the count lives on the device: no host round trip between the launches)
+__global__ void __launch_bounds__(256) k_prune_reinsert(const SubmitParams p, const fa_row *rows)
+{
+    const unsigned long long n = p.tstate->flush_rows;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t key[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) key[k] = rows[i].key[k];
+        table_add<4>(p, key, hash64<4>(key), rows[i].bytes, rows[i].packets, rows[i].count);
     }
 }
 

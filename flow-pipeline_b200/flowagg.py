@@ -25,6 +25,7 @@ FA_CFG_SCALE_SAMPLING = 0x2
 FA_CFG_COLUMNS = 0x4
 FA_CFG_NO_AGGREGATE = 0x8
 FA_CFG_CALLER_STREAM = 0x10
+FA_CFG_TOPK_ONLY = 0x20
 FA_FRAMED = 0x1
 FA_FLUSH_KEEP = 0x1
 FA_FLUSH_UNSORTED = 0x2
@@ -52,7 +53,7 @@ class FlowAggError(RuntimeError):
 class FaConfig(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("key_mode", C.c_uint32), ("flags", C.c_uint32),
                 ("table_capacity", C.c_uint64), ("cms_depth", C.c_uint32), ("cms_width_log2", C.c_uint32),
-                ("max_batch_bytes", C.c_uint64), ("max_batch_records", C.c_uint32), ("reserved0", C.c_uint32),
+                ("max_batch_bytes", C.c_uint64), ("max_batch_records", C.c_uint32), ("topk_k", C.c_uint32),
                 ("stream", C.c_void_p)]
 
 
@@ -181,17 +182,20 @@ class FlowAgg:
     """One fa_ctx: the state of one ConsumeClaim goroutine (inserter.go:75-88,176) on one GPU."""
 
     def __init__(self, key_mode="flows5m", device=0, cms=False, scale_sampling=False, columns=False, aggregate=True,
-                 table_capacity=0, cms_depth=0, cms_width_log2=0, max_batch_bytes=0, max_batch_records=0, stream=None):
+                 table_capacity=0, cms_depth=0, cms_width_log2=0, max_batch_bytes=0, max_batch_records=0, stream=None,
+                 topk_only=False, topk_k=0):
         self._L = load_library()
         self.key_mode = KEY_MODES[key_mode] if isinstance(key_mode, str) else int(key_mode)
         self.kw = KEY_WORDS[self.key_mode]
         flags = (FA_CFG_CMS if cms else 0) | (FA_CFG_SCALE_SAMPLING if scale_sampling else 0) | (FA_CFG_COLUMNS if columns else 0)
+        if topk_only:
+            flags |= FA_CFG_TOPK_ONLY | FA_CFG_CMS
         if not aggregate:
             flags |= FA_CFG_NO_AGGREGATE
         if stream is not None:
             flags |= FA_CFG_CALLER_STREAM  # also when the handle is 0: torch's default stream
         self.cfg = FaConfig(FA_ABI_VERSION, device, self.key_mode, flags, table_capacity, cms_depth, cms_width_log2,
-                            max_batch_bytes, max_batch_records, 0, stream)
+                            max_batch_bytes, max_batch_records, topk_k, stream)
         self.cms_depth = cms_depth or 4
         self.cms_width_log2 = cms_width_log2 or 20
         self._h = C.c_void_p()

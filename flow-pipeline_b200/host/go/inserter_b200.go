@@ -9,8 +9,9 @@
 //     the global mutex (inserter.go:75-88, :92, :115);
 //   - buffer() memcpy's msg.Value into the library's pinned slab instead of
 //     proto.Unmarshal + append (inserter.go:113-165);
-//   - flush() emits flows_5m rows from fa_flush instead of one INSERT per flow
-//     (inserter.go:90-111);
+//   - flush() emits flows_5m rows from fa_flush_begin / fa_flush_end instead of one INSERT per
+//     flow (inserter.go:90-111), on -flush.dur and on -flush.count (inserter.go:36,118,161), without
+//     stalling the claim while the table drains;
 //   - MarkMessage moves after the slab hand-over (inserter.go:188).
 // Flags, logging, metrics endpoint, consumer-group wiring in main() stay as they are.
 //
@@ -46,6 +47,9 @@ type partitionState struct {
 	fill    C.size_t
 	nrec    C.size_t
 	pending []*sarama.ConsumerMessage
+
+	sinceFlush int  // messages buffered since the last flush (-flush.count, inserter.go:118,161)
+	draining   bool // fa_flush_begin issued, its fa_flush_end not yet
 }
 
 func newPartitionState(device int, keyMode C.uint32_t) *partitionState {
@@ -110,6 +114,7 @@ func (ps *partitionState) buffer(session sarama.ConsumerGroupSession, msg *saram
 	}
 	ps.fill += C.size_t(n + len(msg.Value))
 	ps.nrec++
+	ps.sinceFlush++
 	*(*C.uint32_t)(unsafe.Add(unsafe.Pointer(ps.offs), uintptr(ps.nrec)*4)) = C.uint32_t(ps.fill)
 	ps.pending = append(ps.pending, msg)
 }
@@ -126,6 +131,36 @@ func (ps *partitionState) flush(session sarama.ConsumerGroupSession, sink func(r
 	}
 	if rc != C.FA_OK && rc != C.FA_ERR_TABLE_FULL {
 		log.Fatalf("fa_flush: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ps.ctx)))
+	}
+	sink(rows[:n])
+}
+
+// flushBegin / flushEnd: the same flush in two halves (include/flowagg.h).  Between them ConsumeClaim keeps buffering -- the
+// GPU aggregates the new messages into a spare table while the filled one drains on a side stream -- where the
+// reference's flush holds s.lock and stalls every partition (inserter.go:90-111).
+func (ps *partitionState) flushBegin(session sarama.ConsumerGroupSession) {
+	ps.submit(session)
+	if rc := C.fa_flush_begin(ps.ctx, 0); rc != C.FA_OK {
+		log.Fatalf("fa_flush_begin: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ps.ctx)))
+	}
+	ps.draining = true
+	ps.sinceFlush = 0
+}
+
+func (ps *partitionState) flushEnd(sink func(rows []C.fa_row)) {
+	if !ps.draining {
+		return
+	}
+	ps.draining = false
+	rows := make([]C.fa_row, 1<<16)
+	var n C.size_t
+	rc := C.fa_flush_end(ps.ctx, &rows[0], C.size_t(len(rows)), &n)
+	if rc == C.FA_ERR_CAPACITY { // the rows are kept: once more with the size it reported
+		rows = make([]C.fa_row, n)
+		rc = C.fa_flush_end(ps.ctx, &rows[0], n, &n)
+	}
+	if rc != C.FA_OK && rc != C.FA_ERR_TABLE_FULL {
+		log.Fatalf("fa_flush_end: %s (%s)", C.GoString(C.fa_strerror(rc)), C.GoString(C.fa_last_error(ps.ctx)))
 	}
 	sink(rows[:n])
 }
@@ -159,13 +194,20 @@ func (s *state) ConsumeClaimB200(session sarama.ConsumerGroupSession, claim sara
 		select {
 		case message, ok := <-claim.Messages():
 			if !ok {
+				ps.flushEnd(s.writeRows) // a drain still in flight, then the last window in one go
 				ps.flush(session, s.writeRows)
 				return nil
 			}
 			log.Debugf("%s/%d/%d\t%s\t", message.Topic, message.Partition, message.Offset, message.Key)
 			ps.buffer(session, message, s.fixedLen)
+			// -flush.count (inserter.go:36,118,161): a flush every N buffered messages, timer or not
+			if *FlushCount > 0 && ps.sinceFlush >= *FlushCount {
+				ps.flushEnd(s.writeRows)
+				ps.flushBegin(session)
+			}
 		case <-timer:
-			ps.flush(session, s.writeRows)
+			ps.flushEnd(s.writeRows) // the previous window's rows: drained long ago
+			ps.flushBegin(session)   // this window: swap tables and return to the claim at once
 			timer = time.After(*FlushTime)
 		}
 	}

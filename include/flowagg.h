@@ -63,6 +63,13 @@ typedef enum fa_key_mode {
                                       the dashboards' weighting (viz-ch.json:74)          */
 #define FA_CFG_COLUMNS 0x4u      /* also materialise the decoded columns (kernel 1 output) */
 #define FA_CFG_NO_AGGREGATE 0x8u /* decode only (with FA_CFG_COLUMNS): no group table      */
+#define FA_CFG_TOPK_ONLY 0x20u   /* with FA_CFG_CMS and an address key: heavy hitters ONLY (the dashboards' top-N,
+                                    viz-ch.json:233,479).  The sketch sees every flow; a key enters the group table -- now a
+                                    bounded CANDIDATE table -- only once its sketch estimate reaches 1/(64*topk_k) of the weight
+                                    seen so far (at most 64*topk_k keys can truly weigh that much), and leaves again when the
+                                    bar has outgrown it.  Memory no longer depends on the number of distinct keys; fa_topk* work
+                                    as before; fa_flush then returns the candidates with their sums SINCE ADMISSION, not an
+                                    exact roll-up.  table_capacity: at least 4 * 64 * topk_k slots (0 = that).              */
 #define FA_CFG_CALLER_STREAM 0x10u /* run on fa_config.stream even when it is NULL (the legacy
                                       default stream) instead of a private stream           */
 
@@ -77,7 +84,7 @@ typedef struct fa_config {
     uint32_t cms_width_log2; /* 0 = 20  (configs[2]) */
     uint64_t max_batch_bytes;   /* staging for host submits; 0 = 256 MiB */
     uint32_t max_batch_records; /* 0 = 4 Mi */
-    uint32_t reserved0;
+    uint32_t topk_k;         /* FA_CFG_TOPK_ONLY: the K the context will be asked for; 0 = 1000 */
     void *stream; /* cudaStream_t to run on; NULL = a private non-blocking stream.
                      Passing the caller's stream lets the caller order/time work
                      with its own events. */

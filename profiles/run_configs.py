@@ -12,6 +12,13 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import flow_pipeline_b200 as fp  # noqa: E402
 
+ONLY = sys.argv[1:]  # substrings of the config names to run (default: all)
+
+
+def want(name):
+    return not ONLY or any(o in name for o in ONLY)
+
+
 SLAB = 1 << 24
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream().cuda_stream
@@ -21,6 +28,8 @@ out = {}
 
 
 def run(name, agg, cfg, n_total, after=None):
+    if not want(name):
+        return
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range((n_total + SLAB - 1) // SLAB)]
     done = 0
     nbytes = 0
@@ -74,10 +83,36 @@ def topk(a):
             "top1_estimate": int(top["estimate"][0]), "top1_exact": int(exact["bytes"][0])}
 
 
-with fp.FlowAgg("srcaddr", stream=stream, cms=True, cms_depth=4, cms_width_log2=20, table_capacity=1 << 25) as a:
-    run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows", a, cfg, 1_000_000_000, topk)
+EXACT_TOP = {}
+
+
+def topk_exact(a):
+    r = topk(a)
+    rows = a.flush(keep=True, sort=False)
+    exact = rows[np.argsort(-rows["bytes"].astype(np.int64), kind="stable")][:1000]
+    EXACT_TOP["keys"] = {bytes(k.tobytes()) for k in exact["key"]}
+    return r
+
+
+def topk_bounded(a):
+    t0 = time.time()
+    top = a.topk_local(1000)
+    t1 = time.time()
+    res = {"topk_ms": (t1 - t0) * 1e3, "candidates_in_table": int(a.stats()["n_groups"]), "top1_estimate": int(top["estimate"][0])}
+    if "keys" in EXACT_TOP:
+        res["top1000_recall_vs_exact"] = sum(bytes(k.tobytes()) in EXACT_TOP["keys"] for k in top["key"]) / 1000.0
+    return res
+
+
+if want("configs[2]"):
+    with fp.FlowAgg("srcaddr", stream=stream, cms=True, cms_depth=4, cms_width_log2=20, table_capacity=1 << 25) as a:
+        run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, EXACT candidate table (1.6 GB, every key)", a, cfg, 1_000_000_000, topk_exact)
+    # the sketch workload proper: bounded candidate set (FA_CFG_TOPK_ONLY), memory independent of the number of keys
+    with fp.FlowAgg("srcaddr", stream=stream, topk_only=True, topk_k=1000, cms_depth=4, cms_width_log2=20) as a:
+        run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, bounded candidates (FA_CFG_TOPK_ONLY, 12 MiB table)", a, cfg, 1_000_000_000, topk_bounded)
 # configs[4]: 100M unique 5-tuples, HBM open-address table at load 0.37
 cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=250_000, addr_mode=2, framed=True)
-with fp.FlowAgg("5tuple", stream=stream, table_capacity=1 << 28) as a:
-    run("configs[4] 100M unique 5-tuples (2^28-slot table in HBM)", a, cfg, 100_000_000)
+if want("configs[4]"):
+    with fp.FlowAgg("5tuple", stream=stream, table_capacity=1 << 28) as a:
+        run("configs[4] 100M unique 5-tuples (2^28-slot table in HBM)", a, cfg, 100_000_000)
 print(json.dumps(out, indent=1))

@@ -934,3 +934,37 @@ def test_asynchronous_flush_equals_the_synchronous_one(fp, oracle, torch_cuda, m
         with pytest.raises(fp.FlowAggError):
             a.flush()
         assert np.array_equal(a.flush_end(), want[0])
+
+
+@pytest.mark.gpu
+def test_topk_only_keeps_a_bounded_candidate_set(fp, oracle, torch_cuda):
+    """FA_CFG_TOPK_ONLY (BASELINE configs[2] as a real sketch workload): the sketch is bit-equal to the oracle's; the group
+    table only ever holds keys whose estimate reached 1/(64 K) of the weight seen -- far fewer than the distinct keys of the
+    stream, whatever their number -- and the top-K it yields is the oracle's (exact candidates) up to >= 99 % recall, with
+    identical estimates for the keys both report."""
+    cfg = fp.FaMockerConfig.make(seed=31, flows_per_second=5000, addr_mode=fp.FA_ADDR_ZIPF24, framed=True)
+    d, wl, K, n_sub, per = 4, 18, 200, 6, 500_000
+    slabs = [fp.mocker_host(cfg, i * per, per) for i in range(n_sub)]
+    buf = np.concatenate([b for b, _ in slabs])
+    offs = np.concatenate([[0]] + [o[1:].astype(np.int64) + sum(len(bb) for bb, _ in slabs[:i]) for i, (_, o) in enumerate(slabs)]).astype(np.uint32)
+    cand, cms, _ = oracle.run_batch(buf, offs, key_mode="srcaddr", cms=(d, wl))
+    want = oracle.topk(cms, d, wl, 4, cand, K)
+    assert len(cand) > 200_000                                                   # distinct keys of the stream
+    with fp.FlowAgg("srcaddr", topk_only=True, topk_k=K, cms_depth=d, cms_width_log2=wl) as a:
+        for b, o in slabs:                                                       # several submits: the table is pruned after each
+            a.submit(b, o)
+        assert np.array_equal(a.cms_read(), cms)                                 # counters bit-equal, whatever the candidates
+        st = a.stats()
+        assert 0 < st["n_groups"] <= 4 * 64 * 256 and st["n_groups"] < len(cand) // 8   # bounded: 64 K' slots' worth, K' = 2^ceil(log2 K)
+        top = a.topk_local(K)
+    assert len(top) == K
+    got = {bytes(r["key"][:4].tobytes()): int(r["estimate"]) for r in top}
+    exp = {bytes(r["key"][:4].tobytes()): int(r["estimate"]) for r in want}
+    common = set(got) & set(exp)
+    assert len(common) >= 0.99 * K
+    assert all(got[k] == exp[k] for k in common)                                 # same sketch, same estimate
+    # a context may not combine the flag with an exact roll-up's options, and needs an address key
+    for bad in (dict(key_mode="aspair", topk_only=True), dict(key_mode="srcaddr", topk_only=True, scale_sampling=True),
+                dict(key_mode="srcaddr", topk_only=True, table_capacity=1024)):
+        with pytest.raises(fp.FlowAggError):
+            fp.FlowAgg(**bad)
