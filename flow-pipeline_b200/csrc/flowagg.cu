@@ -41,6 +41,7 @@ struct fa_ctx {
     uint64_t capacity = 0;
     bool weighted = false;
     uint32_t admit_shift = 0;  // FA_CFG_TOPK_ONLY: log2(64 * topk_k), 0 otherwise
+    uint32_t hot_slots_per_replica = kHotSlots;
 
     cudaStream_t stream = nullptr;  // compute
     cudaStream_t copy_stream = nullptr;
@@ -161,7 +162,7 @@ static cudaError_t launch_table_init(fa_ctx *c, uint8_t *slots, cudaStream_t str
     k_table_init<KW><<<grid, 256, 0, stream>>>(slots, n_slots);
     c->n_kernels++;
     if (with_hot && c->d_hot) {
-        k_table_init<KW><<<c->num_sms, 256, 0, stream>>>(c->d_hot, (unsigned long long)kHotReplicas * kHotSlots);
+        k_table_init<KW><<<c->num_sms, 256, 0, stream>>>(c->d_hot, (unsigned long long)kHotReplicas * c->hot_slots_per_replica);
         c->n_kernels++;
         c->hot_dirty = false;
     }
@@ -175,6 +176,7 @@ static void fill_table_params(fa_ctx *c, SubmitParams &p)
     p.counters = c->d_counters;
     p.tstate = c->d_ts;
     p.hot_slots = c->d_hot;
+    p.hot_mask = c->hot_slots_per_replica - 1u;
 }
 
 template <int KW>
@@ -376,7 +378,8 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     c->h_ts_drain = c->h_ts + 1;
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
         FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
-        if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * kHotSlots * c->slot_bytes));
+        c->hot_slots_per_replica = c->admit_shift ? kCandHotSlots : kHotSlots;
+        if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * c->hot_slots_per_replica * c->slot_bytes));
         int rc = table_init(c);
         if (rc) return rc;
     }
@@ -550,7 +553,7 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
         if (rc) return rc;
         const int g = (int)std::min<uint64_t>((n_slots + 255) / 256, (uint64_t)c->num_sms * 8);
         // the heavy keys' updates sit in the replicas and their sketch weight in the slots: settle both first
-        k_merge_hot_candidates<<<c->num_sms, 256, 0, c->stream>>>(p, kHotReplicas * kHotSlots);
+        k_merge_hot_candidates<<<c->num_sms * 4, 256, 0, c->stream>>>(p, (unsigned long long)kHotReplicas * c->hot_slots_per_replica);
         k_apply_pending<<<g, 256, 0, c->stream>>>(p, c->capacity);
         c->n_kernels += 2;
         c->hot_dirty = false;

@@ -32,6 +32,7 @@ constexpr int kTileBytesMax = 112 * 1024; // staged bytes per tile, upper bound 
 constexpr uint32_t kHotReplicas = 64;  // CTA b uses replica b mod 64
 constexpr uint32_t kHotSlots = 1024;   // slots per replica (power of two)
 constexpr uint32_t kHotProbes = 8;     // bounded probe sequence; a miss falls through to the main table
+constexpr uint32_t kCandHotSlots = 8192;  // FA_CFG_TOPK_ONLY: slots per replica (twice the candidates a top-1000 context keeps)
 
 // per group table (a context has two: the one being filled and the one being flushed)
 struct TableState {
@@ -66,6 +67,7 @@ struct SubmitParams {
     // sketch (nullptr = off)
     unsigned long long *cms;
     uint32_t cms_depth, cms_wlog2;
+    uint32_t hot_mask;     // slots per hot replica - 1 (kHotSlots - 1; FA_CFG_TOPK_ONLY uses kCandHotSlots - 1)
     uint32_t admit_shift;  // FA_CFG_TOPK_ONLY: a key enters the (bounded) candidate table only once its sketch estimate
                            // reaches total_weight >> admit_shift; 0 = every key is a candidate (the exact group table)
     Counters *counters;
@@ -467,12 +469,12 @@ __device__ __forceinline__ void slot_add_pending(uint8_t *s, unsigned long long 
     red_add_u64(v + 3, weight);
 }
 
-__device__ __forceinline__ bool hot_add_pending(uint8_t *replica, unsigned long long klo, unsigned long long khi, unsigned long long h,
-                                                unsigned long long bytes, unsigned long long packets, unsigned long long weight)
+__device__ __forceinline__ bool hot_add_pending(uint8_t *replica, uint32_t hot_mask, unsigned long long klo, unsigned long long khi,
+                                                unsigned long long h, unsigned long long bytes, unsigned long long packets, unsigned long long weight)
 {
-    uint32_t slot = (uint32_t)(h >> 20) & (kHotSlots - 1u);
+    uint32_t slot = (uint32_t)(h >> 20) & hot_mask;
 #pragma unroll 1
-    for (uint32_t probe = 0; probe < kHotProbes; probe++) {
+    for (uint32_t probe = 0; probe < 4u; probe++) {
         uint8_t *s = replica + (size_t)slot * SlotLayout<4>::BYTES;
         unsigned long long clo, chi;
         ld_relaxed_u128(s, clo, chi);
@@ -487,7 +489,7 @@ __device__ __forceinline__ bool hot_add_pending(uint8_t *replica, unsigned long 
             slot_add_pending(s, bytes, packets, 1ull, weight);
             return true;
         }
-        slot = (slot + 1) & (kHotSlots - 1u);
+        slot = (slot + 1) & hot_mask;
     }
     return false;
 }
@@ -497,7 +499,7 @@ __device__ __forceinline__ bool hot_add_pending(uint8_t *replica, unsigned long 
 // Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
 template <int MODE>
 __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have,
-                                                   unsigned long long &total_w)
+                                                   unsigned long long &total_w, const unsigned long long admit_bar = 0)
 {
     constexpr int KW = KeyTraits<MODE>::KW;
     uint32_t key[KW];
@@ -523,12 +525,12 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
             // already a candidate (a heavy key): slot and sketch weight through the CTA's replica; the sketch is settled after the launch
             bool done = false;
             if (p.hot_slots)
-                done = hot_add_pending(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<4>::BYTES, klo, khi, h, b, pk, w);
+                done = hot_add_pending(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * ((size_t)p.hot_mask + 1u) * SlotLayout<4>::BYTES, p.hot_mask,
+                                       klo, khi, h, b, pk, w);
             if (!done) slot_add_pending(cs, b, pk, 1ull, w);
         } else {
             const unsigned long long est = cms_add_estimate(p, h, w);
-            const unsigned long long seen = __ldg(&p.counters->total_weight);  // as of this launch's start (nothing writes it meanwhile)
-            if (p.slots && est >= (seen >> p.admit_shift)) candidate_add(p, key, h, b, pk, 1ull);
+            if (p.slots && est >= admit_bar) candidate_add(p, key, h, b, pk, 1ull);
         }
         total_w += w;
         return (uint32_t)h;
@@ -655,17 +657,26 @@ struct AggConsumer {
         uint32_t h32;
         bool have;
         unsigned long long weight;  // sketched weight of the record (FA_CFG_TOPK_ONLY keeps the running total)
+        unsigned long long bar;     // FA_CFG_TOPK_ONLY: estimate a key needs to become a candidate in this launch
     };
+    // total weight seen before this launch >> admit_shift (nothing writes total_weight while the launch runs); loaded once,
+    // early, so that its latency hides behind the tile copy
+    static __device__ __forceinline__ unsigned long long admit_bar(const SubmitParams &p)
+    {
+        return (KW == 4 && WEIGHTED && p.admit_shift) ? (__ldg(&p.counters->total_weight) >> p.admit_shift) : 0ull;
+    }
     static __device__ __forceinline__ void item_clear(Item &it)
     {
         it.h32 = 0;
         it.have = false;
         it.weight = 0;
+        it.bar = 0;
     }
     static __device__ __forceinline__ void add_weight_one(const SubmitParams &p, const Item &it)  // a record parsed out of line
     {
         if (KW == 4 && WEIGHTED && p.admit_shift && it.weight) atomicAdd(&p.counters->total_weight_acc, it.weight);
     }
+    static __device__ __forceinline__ void set_bar(Item &it, unsigned long long bar) { it.bar = bar; }
     // the tile's sketched weight into the context's running total (one atomic per warp)
     static __device__ __forceinline__ void add_weight(const SubmitParams &p, const Item &it)
     {
@@ -686,7 +697,7 @@ struct AggConsumer {
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have, it.weight);
+            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have, it.weight, it.bar);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
@@ -723,6 +734,8 @@ struct ColConsumer {
     static __device__ __forceinline__ void sample_repeats(const SubmitParams &, const Item &) {}
     static __device__ __forceinline__ void add_weight(const SubmitParams &, const Item &) {}
     static __device__ __forceinline__ void add_weight_one(const SubmitParams &, const Item &) {}
+    static __device__ __forceinline__ unsigned long long admit_bar(const SubmitParams &) { return 0ull; }
+    static __device__ __forceinline__ void set_bar(Item &, unsigned long long) {}
     static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool, Item &)
     {
         consume(tp, r, ok, f, bad, nokey);
@@ -782,6 +795,7 @@ __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32
     }
     typename Consumer::Item it;
     Consumer::item_clear(it);
+    Consumer::set_bar(it, Consumer::admit_bar(tp.p));
     Consumer::consume(tp, r, ok, f, bad, nokey, false, it);
     Consumer::add_weight_one(tp.p, it);
     return bad | (nokey << 1);
@@ -820,6 +834,7 @@ __global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / T
     const SubmitParams &p = tp.p;
     const TileInfo t = stage_tile(p, blockIdx.x, smem);
     const bool hot = Consumer::want_hot(p);  // uniform over the grid; the load overlaps the tile copy
+    const unsigned long long bar = Consumer::admit_bar(p);
     uint32_t bad = 0, nokey = 0;
     uint32_t in_tile = threadIdx.x;
     // full tiles only (the mapping is a bijection on [0, THREADS)); short tails keep the identity
@@ -834,6 +849,7 @@ __global__ void __launch_bounds__(THREADS, (Consumer::MIN_BLOCKS * kThreads) / T
     mbar_wait(smem_u32(smem + p.tile_bytes + kTilePad), 0);
     typename Consumer::Item item;
     Consumer::item_clear(item);
+    Consumer::set_bar(item, bar);
     if (active) {
         if (o0 >= t.b0 && o0 <= o1 && o1 <= t.s_end) {
             Flow f;
@@ -888,7 +904,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
             f.dst_len = c.dst_addr_len[r] == 255 ? 17u : c.dst_addr_len[r];
         }
         bool have;
-        aggregate_flow<MODE>(p, f, nokey, false, have, wsum);
+        aggregate_flow<MODE>(p, f, nokey, false, have, wsum, p.admit_shift ? (__ldg(&p.counters->total_weight) >> p.admit_shift) : 0ull);
     }
     if (wsum) atomicAdd(&p.counters->total_weight_acc, wsum);
     flush_counts(p, 0, nokey);
@@ -994,9 +1010,9 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsi
 // threshold -- keys admitted early, when little had been seen and the bar was low, leave again.  Three launches over
 // <= table_capacity slots: collect survivors, empty the table, re-insert.
 // fold the replicas' candidate updates (sums + pending sketch weight) into the main candidate table, empty the replicas
-__global__ void __launch_bounds__(256) k_merge_hot_candidates(const SubmitParams p, uint32_t n_hot_slots)
+__global__ void __launch_bounds__(256) k_merge_hot_candidates(const SubmitParams p, unsigned long long n_hot_slots)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hot_slots; i += gridDim.x * blockDim.x) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_hot_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
         uint8_t *s = p.hot_slots + (size_t)i * SlotLayout<4>::BYTES;
         unsigned long long *w = reinterpret_cast<unsigned long long *>(s);
         const unsigned long long klo = w[0], khi = w[1];
