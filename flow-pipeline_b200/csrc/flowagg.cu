@@ -120,7 +120,7 @@ struct fa_ctx {
 
 static const int k_key_words[FA_KEY_MODES] = {4, 2, 4, 4, 11, 1, 1};
 
-static uint32_t slot_bytes_for(int kw) { return kw <= 2 ? 32u : (kw == 4 ? 48u : 72u); }
+static uint32_t slot_bytes_for(int kw) { return kw <= 2 ? 32u : (kw == 4 ? 48u : 32u); }  // wide keys: the head; the key records sit behind the heads (table_alloc_bytes)
 
 extern "C" const char *fa_strerror(int s)
 {
@@ -377,7 +377,7 @@ extern "C" int fa_create(const fa_config *cfg, fa_ctx **out)
     memset(c->h_ts, 0, 2 * sizeof(TableState));
     c->h_ts_drain = c->h_ts + 1;
     if (!(c->cfg.flags & FA_CFG_NO_AGGREGATE)) {
-        FA_CUDA(c, cudaMalloc(&c->d_slots, (c->capacity + 1) * c->slot_bytes));  // + the side slot
+        FA_CUDA(c, cudaMalloc(&c->d_slots, table_alloc_bytes(c->kw, c->capacity + 1)));  // + the side slot
         c->hot_slots_per_replica = c->admit_shift ? kCandHotSlots : kHotSlots;
         if (c->kw <= 4) FA_CUDA(c, cudaMalloc(&c->d_hot, (size_t)kHotReplicas * c->hot_slots_per_replica * c->slot_bytes));
         int rc = table_init(c);
@@ -504,6 +504,7 @@ static int launch_batch(fa_ctx *c, const uint8_t *d_buf, uint64_t base, uint64_t
     p.cms_wlog2 = c->cfg.cms_width_log2;
     p.admit_shift = c->admit_shift;
     p.hint_set = (uint32_t)(c->n_submits & 1u);
+    p.sample_seed = (uint32_t)c->n_submits * 0x85EBCA6Bu;
     if (c->d_hot) c->hot_dirty = true;
     FA_CUDA(c, cudaMemsetAsync(&c->d_counters->hint[p.hint_set][0], 0, 8, c->stream));  // this submit's statistics start at zero
     // tile shape from the batch's mean record size: 256 records per CTA when their bytes fit
@@ -1009,7 +1010,7 @@ extern "C" int fa_flush_begin(fa_ctx *c, uint32_t flags)
         FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_swap, cudaEventDisableTiming));
         FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_spare_ready, cudaEventDisableTiming));
         FA_CUDA(c, cudaEventCreateWithFlags(&c->ev_flush_done, cudaEventDisableTiming | cudaEventBlockingSync));
-        FA_CUDA(c, cudaMalloc(&c->d_slots_spare, (c->capacity + 1) * c->slot_bytes));
+        FA_CUDA(c, cudaMalloc(&c->d_slots_spare, table_alloc_bytes(c->kw, c->capacity + 1)));
         FA_CUDA(c, cudaMalloc(&c->d_ts_spare, sizeof(TableState)));
         FA_CUDA(c, cudaMemsetAsync(c->d_ts_spare, 0, sizeof(TableState), c->flush_stream));
         int rc0 = table_init_at(c, c->d_slots_spare, c->flush_stream, false);

@@ -73,6 +73,7 @@ struct SubmitParams {
     Counters *counters;
     TableState *tstate;  // of the table behind `slots`
     uint32_t hint_set;  // this submit writes counters->hint[hint_set], reads hint[hint_set ^ 1]
+    uint32_t sample_seed;  // FA_CFG_TOPK_ONLY: distinguishes the submits in the admission draw (a function of the submit's number)
     // hot-key replicas: kHotReplicas small tables of kHotSlots slots (same slot layout as the main table)
     uint8_t *hot_slots;
 };
@@ -153,21 +154,57 @@ __host__ __device__ __forceinline__ unsigned long long hash64(const uint32_t *ke
     return h;
 }
 
+// Where a key lives in ITS OWN group table (and hot replica).  Nothing outside the library sees this value -- the sketch rows
+// and the box-wide owner of a key come from hash64, which the checker restates -- so narrow keys (one or two words: AS pairs,
+// ports) take a 6-instruction multiplicative mix instead of hash64's 40: the table index reads bits 32.., the replica index
+// bits 20.., both fed by every key bit.
+template <int KW>
+__device__ __forceinline__ unsigned long long slot_hash(const uint32_t *key)
+{
+#ifdef FA_CHEAP_SLOT_HASH
+    if (KW <= 2) {
+        const uint32_t a = key[0] * 0x9E3779B1u;
+        const uint32_t b = KW == 2 ? key[KW == 2 ? 1 : 0] * 0x85EBCA77u : 0x27D4EB2Fu;
+        const uint32_t x = a ^ __funnelshift_l(b, b, 17);
+        return (unsigned long long)x * 0xD6E8FEB86659FD93ull;
+    }
+#endif
+    return hash64<KW>(key);
+}
+
 // ---- group table: open addressing, linear probing, in HBM (L2-resident when small) ---
 //
 // Three slot layouts, all with values {u64 bytes, packets, count} behind the key:
 //   KW <= 2   32 B  { u64 key | 3 x u64 }            claimed by a 64-bit CAS on the key
 //   KW == 4   48 B  { u128 key | 3 x u64 | pad }     claimed by a 128-bit CAS on the key
-//   KW == 11  72 B  { u32 state, u32 key[11] | 3 x u64 }   claimed through a state word
+//   KW == 11  split: a 32-byte HEAD per slot { u64 head = fingerprint << 32 | state | 3 x u64 } in one array and,
+//             behind all heads, a 64-byte KEY record per slot { u32 key[11], zero pad } in a second, 64-byte-aligned array
 // For the CAS layouts the all-ones key marks an empty slot; the one real key that
 // is all ones lives in a reserved side slot behind the table (index = capacity).
 // One 32-byte sector per record for the AS-pair roll-up.  Lookups are relaxed
 // GPU-scope loads served by L2 (no L1 invalidation on the hot path).
+//
+// The wide-key table is sized for HBM, not L2 (BASELINE configs[4]: 100 M distinct 5-tuples), so it is laid out by DRAM
+// sector: a probe reads ONE sector (the head); the fingerprint (the hash bits the slot index does not use) settles a
+// mismatch without touching the key; a claim writes the key record as four 16-byte stores that cover both of its sectors
+// completely (no read-for-ownership), and the three sums land in the head sector the probe already brought into L2.
+// Insert = 32 B read + 96 B written back; a repeated key = head + key record read.  (Round 1's 72-byte slot straddled
+// three sectors and cost ~6 sector reads + 3 write-backs per insert, ncu: profiles/r02/experiments.)
 template <int KW> struct SlotLayout;
 template <> struct SlotLayout<1> { static constexpr uint32_t BYTES = 32, VAL_OFF = 8; };
 template <> struct SlotLayout<2> { static constexpr uint32_t BYTES = 32, VAL_OFF = 8; };
 template <> struct SlotLayout<4> { static constexpr uint32_t BYTES = 48, VAL_OFF = 16; };
-template <> struct SlotLayout<11> { static constexpr uint32_t BYTES = 72, VAL_OFF = 48; };
+template <> struct SlotLayout<11> { static constexpr uint32_t BYTES = 32, VAL_OFF = 8; };  // the head array; keys: wide_key_*
+constexpr uint32_t kWideKeyBytes = 64;
+// byte offset of the key array behind n_slots heads (n_slots counts the side slot, which wide keys never use)
+__host__ __device__ __forceinline__ unsigned long long wide_key_offset(unsigned long long n_slots) { return (n_slots * 32ull + 127ull) & ~127ull; }
+// allocation size of a table of n_slots slots
+__host__ __device__ __forceinline__ unsigned long long table_alloc_bytes(int kw, unsigned long long n_slots)
+{
+    if (kw <= 2) return n_slots * 32ull;
+    if (kw == 4) return n_slots * 48ull;
+    return wide_key_offset(n_slots) + n_slots * kWideKeyBytes;
+}
 enum : uint32_t { SLOT_EMPTY = 0, SLOT_BUSY = 1, SLOT_READY = 2 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const void *p)
@@ -186,15 +223,25 @@ __device__ __forceinline__ void ld_relaxed_u128(const void *p, unsigned long lon
 {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_u32(const void *p)
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const void *p)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(void *p, uint32_t v)
+__device__ __forceinline__ void st_release_u64(void *p, unsigned long long v)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
 {
@@ -287,41 +334,43 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
             slot = (slot + 1) & p.slot_mask;
         }
     } else {
-        // wide keys (5-tuple): EMPTY -> BUSY (CAS) -> key written -> READY (release)
+        // wide keys (5-tuple): head EMPTY(0) -> fingerprint|BUSY (CAS) -> key record written -> fingerprint|READY (release)
+        const unsigned long long fp = h << 32;  // lo32(h): the slot index comes from hi32(h)
+        uint8_t *keys = p.slots + wide_key_offset((unsigned long long)p.slot_mask + 2ull);
+        uint32_t kk[11];
+#pragma unroll
+        for (int i = 0; i < 11; i++) kk[i] = i < KW ? key[i < KW ? i : 0] : 0u;
 #pragma unroll 1
         for (uint32_t probe = 0; probe <= p.slot_mask; probe++) {
             uint8_t *s = p.slots + (size_t)slot * SlotLayout<KW>::BYTES;
-            uint32_t *state = reinterpret_cast<uint32_t *>(s);
-            uint32_t *skey = state + 1;
-            uint32_t st = ld_relaxed_u32(state);
-            if (st == SLOT_EMPTY) {
-                const uint32_t old = atomicCAS(state, (uint32_t)SLOT_EMPTY, (uint32_t)SLOT_BUSY);
-                if (old == SLOT_EMPTY) {
-#pragma unroll
-                    for (int i = 0; i < KW; i++) skey[i] = key[i];
-                    st_release_u32(state, SLOT_READY);
+            uint8_t *kr = keys + (size_t)slot * kWideKeyBytes;
+            unsigned long long hd = ld_relaxed_u64(s);
+            if (hd == 0ull) {
+                hd = atomicCAS(reinterpret_cast<unsigned long long *>(s), 0ull, fp | SLOT_BUSY);
+                if (hd == 0ull) {
+                    // ours: four 16-byte stores cover both sectors of the key record, so L2 never has to fetch them
+                    st_v4(kr, kk[0], kk[1], kk[2], kk[3]);
+                    st_v4(kr + 16, kk[4], kk[5], kk[6], kk[7]);
+                    st_v4(kr + 32, kk[8], kk[9], kk[10], 0u);
+                    st_v4(kr + 48, 0u, 0u, 0u, 0u);
+                    st_release_u64(s, fp | SLOT_READY);
                     atomicAdd(&p.tstate->n_groups, 1ull);
                     return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
                 }
-                st = old;
             }
-            while (st != SLOT_READY) {  // another thread is publishing this slot's key
-                __nanosleep(32);
-                st = ld_acquire_u32(state);
+            // the fingerprint is in place from the claim on: a different one settles the mismatch without reading the key
+            // (and without waiting for a slot that is still being published)
+            if ((hd & 0xFFFFFFFF00000000ull) == fp) {
+                // the key record is ordered behind the publisher's stores only through an acquire load of READY
+                do {
+                    hd = ld_acquire_u64(s);
+                    if ((uint32_t)hd != SLOT_READY) __nanosleep(32);
+                } while ((uint32_t)hd != SLOT_READY);
+                const uint4 k0 = ld_relaxed_v4(kr), k1 = ld_relaxed_v4(kr + 16), k2 = ld_relaxed_v4(kr + 32);
+                const bool same = k0.x == kk[0] && k0.y == kk[1] && k0.z == kk[2] && k0.w == kk[3] && k1.x == kk[4] && k1.y == kk[5] &&
+                                  k1.z == kk[6] && k1.w == kk[7] && k2.x == kk[8] && k2.y == kk[9] && k2.z == kk[10];
+                if (same) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
             }
-            // READY may have been seen through a relaxed load: the key words read next are then not ordered behind the
-            // publisher's stores by the memory model.  A match needs no more (the words equal ours, whoever wrote them); a
-            // MISmatch is only believed after the state has been re-read with acquire and the key compared again.
-            bool same = true;
-#pragma unroll
-            for (int i = 0; i < KW; i++) same &= (ld_relaxed_u32(skey + i) == key[i]);
-            if (!same) {
-                while (ld_acquire_u32(state) != SLOT_READY) __nanosleep(32);
-                same = true;
-#pragma unroll
-                for (int i = 0; i < KW; i++) same &= (ld_relaxed_u32(skey + i) == key[i]);
-            }
-            if (same) return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
             slot = (slot + 1) & p.slot_mask;
         }
     }
@@ -499,7 +548,7 @@ __device__ __forceinline__ bool hot_add_pending(uint8_t *replica, uint32_t hot_m
 // Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
 template <int MODE>
 __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have,
-                                                   unsigned long long &total_w, const unsigned long long admit_bar = 0)
+                                                   unsigned long long &total_w, const unsigned long long admit_bar = 0, const uint32_t rec = 0)
 {
     constexpr int KW = KeyTraits<MODE>::KW;
     uint32_t key[KW];
@@ -508,7 +557,14 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         nokey++;
         return 0u;
     }
+#ifdef FA_CHEAP_SLOT_HASH
+    // narrow keys: the sketch hash only when a sketch is attached (uniform over the grid)
+    const unsigned long long hs = slot_hash<KW>(key);
+    const unsigned long long h = KW > 2 ? hash64<KW>(key) : hs;  // narrow keys: hash64 only inside the sketch branch below
+#else
     const unsigned long long h = hash64<KW>(key);
+    const unsigned long long hs = h;
+#endif
     unsigned long long b = f.bytes, pk = f.packets;
     if (p.scale) {  // sum(Bytes*SamplingRate): viz-ch.json:74
         b *= f.sampling_rate;
@@ -529,8 +585,23 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
                                        klo, khi, h, b, pk, w);
             if (!done) slot_add_pending(cs, b, pk, 1ull, w);
         } else {
+#ifdef FA_ADMIT_ESTIMATE
+            // round-2 first version: admit on the estimate the update itself returns (four RETURNING atomics per flow)
             const unsigned long long est = cms_add_estimate(p, h, w);
             if (p.slots && est >= admit_bar) candidate_add(p, key, h, b, pk, 1ull);
+#else
+            // sample and hold (Estan & Varghese): the sketch takes the flow through fire-and-forget reductions, and the flow
+            // makes its key a candidate with probability min(1, w / bar), bar = total weight / (64 K) -- at most 64 K
+            // admissions are expected per launch whatever the number of keys, and a key that weighs several bars (every
+            // top-K key does) is admitted with probability 1 - exp(-weight / bar).  The draw is a hash of (key, record
+            // number, submit number): the same stream admits the same keys on every run.
+            cms_add(p, h, w);
+            uint32_t u = (uint32_t)(h >> 11) ^ (rec * 0x9E3779B9u) ^ p.sample_seed;
+            u ^= u >> 16; u *= 0x7FEB352Du; u ^= u >> 15; u *= 0x846CA68Bu; u ^= u >> 16;
+            const unsigned long long lo = (unsigned long long)u * admit_bar, hi = __umul64hi((unsigned long long)u, admit_bar);
+            const bool admit = w >= admit_bar || hi < (w >> 32) || (hi == (w >> 32) && lo < (w << 32));   // u / 2^32 < w / bar
+            if (p.slots && admit) candidate_add(p, key, h, b, pk, 1ull);
+#endif
         }
         total_w += w;
         return (uint32_t)h;
@@ -538,11 +609,15 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
     if (p.slots) {
         bool done = false;
         if (KW <= 4 && hot)
-            done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, h, b, pk);
-        if (!done) table_add<KW>(p, key, h, b, pk, 1ull);
+            done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, hs, b, pk);
+        if (!done) table_add<KW>(p, key, hs, b, pk, 1ull);
     }
+#ifdef FA_CHEAP_SLOT_HASH
+    if (p.cms) cms_add(p, KW > 2 ? h : hash64<KW>(key), f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
+#else
     if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
-    return (uint32_t)h;
+#endif
+    return (uint32_t)(hs >> 32);
 }
 
 // ---- tile staging: one bulk-async copy per tile ----------------------------------------------
@@ -692,12 +767,12 @@ struct AggConsumer {
         const unsigned int d = __ldg(&p.counters->hint[p.hint_set ^ 1u][0]), n = __ldg(&p.counters->hint[p.hint_set ^ 1u][1]);
         return n != 0u && d * 16u >= n;  // >= 1/16 of the sampled lanes repeat
     }
-    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
+    static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
                                                    Item &it)
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have, it.weight, it.bar);
+            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have, it.weight, it.bar, r);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
@@ -904,7 +979,7 @@ __global__ void __launch_bounds__(kThreads) k_aggregate_columns(const SubmitPara
             f.dst_len = c.dst_addr_len[r] == 255 ? 17u : c.dst_addr_len[r];
         }
         bool have;
-        aggregate_flow<MODE>(p, f, nokey, false, have, wsum, p.admit_shift ? (__ldg(&p.counters->total_weight) >> p.admit_shift) : 0ull);
+        aggregate_flow<MODE>(p, f, nokey, false, have, wsum, p.admit_shift ? (__ldg(&p.counters->total_weight) >> p.admit_shift) : 0ull, r);
     }
     if (wsum) atomicAdd(&p.counters->total_weight_acc, wsum);
     flush_counts(p, 0, nokey);
@@ -944,7 +1019,7 @@ __global__ void __launch_bounds__(256) k_merge_hot(const SubmitParams p, uint32_
             key[KW == 4 ? 3 : 0] = (uint32_t)(w[KEY64 - 1] >> 32);
         }
         const unsigned long long *v = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
-        table_add<KW>(p, key, hash64<KW>(key), v[0], v[1], v[2]);
+        table_add<KW>(p, key, slot_hash<KW>(key), v[0], v[1], v[2]);
 #pragma unroll
         for (int k = 0; k < KEY64; k++) w[k] = ~0ull;
         unsigned long long *vv = reinterpret_cast<unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
@@ -952,29 +1027,32 @@ __global__ void __launch_bounds__(256) k_merge_hot(const SubmitParams p, uint32_
     }
 }
 
-// is_side: the reserved slot behind the table (the all-ones key); it is occupied iff side_claimed (counters->side_state,
-// which is what n_groups counted) -- its count alone would miss a key whose merged count is 0.
+// Slot i of a table of n_slots (the last one is the reserved side slot of the all-ones key; it is occupied iff
+// side_claimed -- counters->side_state, which is what n_groups counted: its count alone would miss a key whose merged
+// count is 0).  Returns whether the slot holds a group; `vals` = its three sums.
 template <int KW>
-__device__ __forceinline__ bool slot_read(const uint8_t *s, bool is_side, bool side_claimed, uint32_t *key)
+__device__ __forceinline__ bool slot_read(const uint8_t *slots, unsigned long long n_slots, unsigned long long i, bool side_claimed, uint32_t *key,
+                                          const unsigned long long *&vals)
 {
+    const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
+    const bool is_side = i == n_slots - 1;
+    vals = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
     if (KW <= 2) {
         const unsigned long long k = *reinterpret_cast<const unsigned long long *>(s);
         key[0] = (uint32_t)k;
-        if (KW == 2) key[1] = (uint32_t)(k >> 32);
-        const unsigned long long cnt = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF)[2];
-        (void)cnt;
+        if (KW == 2) key[KW == 2 ? 1 : 0] = (uint32_t)(k >> 32);
         return is_side ? side_claimed : k != ~0ull;
     } else if (KW == 4) {
         const unsigned long long lo = reinterpret_cast<const unsigned long long *>(s)[0], hi = reinterpret_cast<const unsigned long long *>(s)[1];
-        key[0] = (uint32_t)lo; key[1] = (uint32_t)(lo >> 32); key[2] = (uint32_t)hi; key[3] = (uint32_t)(hi >> 32);
-        const unsigned long long cnt = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF)[2];
-        (void)cnt;
+        key[0] = (uint32_t)lo; key[KW == 4 ? 1 : 0] = (uint32_t)(lo >> 32); key[KW == 4 ? 2 : 0] = (uint32_t)hi; key[KW == 4 ? 3 : 0] = (uint32_t)(hi >> 32);
         return is_side ? side_claimed : (lo & hi) != ~0ull;
     } else {
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(s);
+        const unsigned long long hd = *reinterpret_cast<const unsigned long long *>(s);
+        if (is_side || (uint32_t)hd != SLOT_READY) return false;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(slots + wide_key_offset(n_slots) + i * kWideKeyBytes);
 #pragma unroll
-        for (int k = 0; k < KW; k++) key[k] = w[1 + k];
-        return !is_side && w[0] == SLOT_READY;
+        for (int k = 0; k < KW; k++) key[k] = w[k];
+        return true;
     }
 }
 
@@ -983,9 +1061,9 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsi
                                                       unsigned long long cap, TableState *counters)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
         uint32_t key[KW];
-        if (!slot_read<KW>(s, i == n_slots - 1, counters->side_state != 0u, key)) continue;
+        const unsigned long long *v;
+        if (!slot_read<KW>(slots, n_slots, i, counters->side_state != 0u, key, v)) continue;
         if (i == n_slots - 1) {  // the side slot holds the all-ones key
 #pragma unroll
             for (int k = 0; k < KW; k++) key[k] = 0xFFFFFFFFu;
@@ -995,7 +1073,6 @@ __global__ void __launch_bounds__(256) k_compact_rows(const uint8_t *slots, unsi
         fa_row r;
 #pragma unroll
         for (int k = 0; k < FA_MAX_KEY_WORDS; k++) r.key[k] = k < KW ? key[k] : 0u;
-        const unsigned long long *v = reinterpret_cast<const unsigned long long *>(s + SlotLayout<KW>::VAL_OFF);
         r.bytes = v[0];
         r.packets = v[1];
         r.count = v[2];
@@ -1059,9 +1136,9 @@ __global__ void __launch_bounds__(256) k_prune_collect(const uint8_t *slots, uns
 {
     const unsigned long long bar = counters->total_weight >> admit_shift;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint8_t *s = slots + i * SlotLayout<4>::BYTES;
         uint32_t key[4];
-        if (!slot_read<4>(s, i == n_slots - 1, ts->side_state != 0u, key)) continue;
+        const unsigned long long *v;
+        if (!slot_read<4>(slots, n_slots, i, ts->side_state != 0u, key, v)) continue;
         if (i == n_slots - 1) key[0] = key[1] = key[2] = key[3] = 0xFFFFFFFFu;
         const unsigned long long h = hash64<4>(key);
         const uint32_t a = (uint32_t)h, b = (uint32_t)(h >> 32) | 1u, mask = (1u << wlog2) - 1u;
@@ -1075,7 +1152,6 @@ __global__ void __launch_bounds__(256) k_prune_collect(const uint8_t *slots, uns
         fa_row r;
 #pragma unroll
         for (int k = 0; k < FA_MAX_KEY_WORDS; k++) r.key[k] = k < 4 ? key[k] : 0u;
-        const unsigned long long *v = reinterpret_cast<const unsigned long long *>(s + SlotLayout<4>::VAL_OFF);
         r.bytes = v[0];
         r.packets = v[1];
         r.count = v[2];
@@ -1112,7 +1188,7 @@ __global__ void __launch_bounds__(256) k_add_rows(const SubmitParams p, const fa
         for (int k = 0; k < KW; k++) key[k] = rows[i].key[k];
         const unsigned long long h = hash64<KW>(key);
         if (n_owners > 1u && key_owner(h, n_owners) != owner) continue;
-        table_add<KW>(p, key, h, rows[i].bytes, rows[i].packets, rows[i].count);
+        table_add<KW>(p, key, slot_hash<KW>(key), rows[i].bytes, rows[i].packets, rows[i].count);
     }
 }
 
@@ -1123,9 +1199,9 @@ __global__ void __launch_bounds__(256) k_estimate(const uint8_t *slots, unsigned
                                                   TableState *counters)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint8_t *s = slots + i * SlotLayout<KW>::BYTES;
         uint32_t key[KW];
-        if (!slot_read<KW>(s, i == n_slots - 1, counters->side_state != 0u, key)) continue;
+        const unsigned long long *v;
+        if (!slot_read<KW>(slots, n_slots, i, counters->side_state != 0u, key, v)) continue;
         if (i == n_slots - 1) {
 #pragma unroll
             for (int k = 0; k < KW; k++) key[k] = 0xFFFFFFFFu;

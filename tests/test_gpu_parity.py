@@ -292,6 +292,26 @@ def test_table_full_is_reported_not_silent(fp, torch_cuda):
         assert len(rows) == 1024 and rows["count"].sum() == 1024
 
 
+def test_wide_key_table_at_high_load_with_repeats(fp, oracle, torch_cuda):
+    """The 5-tuple table (heads + key records, fingerprint-filtered probes): 3 500 distinct keys in 4 096 slots -- long probe
+    chains, every probe passing occupied heads of other keys -- each key seen three times over three submits, so the repeat
+    path (fingerprint match -> acquire -> key record compare) carries two thirds of the updates.  Rows == oracle, bytewise."""
+    cfg = fp.FaMockerConfig.make(seed=77, flows_per_second=10, addr_mode=2, framed=True)
+    buf, offs = fp.mocker_host(cfg, 0, 3500)
+    blob = np.concatenate([buf, buf, buf])
+    o = np.concatenate([offs, offs[1:] + offs[-1], offs[1:] + 2 * offs[-1]]).astype(np.uint32)
+    want, _, res = oracle.run_batch(blob, o, framed=True, key_mode="5tuple")
+    assert len(want) == 3500 and res["n_bad"] == 0
+    with fp.FlowAgg("5tuple", table_capacity=4096) as a:
+        for _ in range(3):
+            a.submit(buf, offs, framed=True)
+        st = a.stats()
+        rows = a.flush()
+    assert st["n_groups"] == 3500 and st["n_dropped"] == 0
+    assert np.array_equal(rows, want)
+    assert (rows["count"] == 3).all()
+
+
 def test_box_topk_single_process_multi_gpu(fp, oracle, torch_cuda):
     if torch_cuda.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
