@@ -186,8 +186,8 @@ __device__ __forceinline__ unsigned long long slot_hash(const uint32_t *key)
 //
 // The wide-key table is sized for HBM, not L2 (BASELINE configs[4]: 100 M distinct 5-tuples), so it is laid out by DRAM
 // sector: a probe reads ONE sector (the head); the fingerprint (the hash bits the slot index does not use) settles a
-// mismatch without touching the key; a claim writes the key record as four 16-byte stores that cover both of its sectors
-// completely (no read-for-ownership), and the three sums land in the head sector the probe already brought into L2.
+// mismatch without touching the key; a claim writes the key record as two 256-bit stores, one whole sector each
+// (no read-for-ownership: measured, four 16-byte stores still made L2 fetch both sectors), and the three sums land in the head sector the probe already brought into L2.
 // Insert = 32 B read + 96 B written back; a repeated key = head + key record read.  (Round 1's 72-byte slot straddled
 // three sectors and cost ~6 sector reads + 3 write-backs per insert, ncu: profiles/r02/experiments.)
 template <int KW> struct SlotLayout;
@@ -239,9 +239,12 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void *p)
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+// one 256-bit store (sm_100: SASS STG.E.ENL2.256): a whole, aligned 32-byte sector in a single request, so L2 has
+// nothing to merge and nothing to fetch before it can write the sector back
+__device__ __forceinline__ void st_sector(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h)
 {
-    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+                 : "memory");
 }
 __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
 {
@@ -348,11 +351,9 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
             if (hd == 0ull) {
                 hd = atomicCAS(reinterpret_cast<unsigned long long *>(s), 0ull, fp | SLOT_BUSY);
                 if (hd == 0ull) {
-                    // ours: four 16-byte stores cover both sectors of the key record, so L2 never has to fetch them
-                    st_v4(kr, kk[0], kk[1], kk[2], kk[3]);
-                    st_v4(kr + 16, kk[4], kk[5], kk[6], kk[7]);
-                    st_v4(kr + 32, kk[8], kk[9], kk[10], 0u);
-                    st_v4(kr + 48, 0u, 0u, 0u, 0u);
+                    // ours: two whole-sector stores write the key record, so L2 never has to fetch it
+                    st_sector(kr, kk[0], kk[1], kk[2], kk[3], kk[4], kk[5], kk[6], kk[7]);
+                    st_sector(kr + 32, kk[8], kk[9], kk[10], 0u, 0u, 0u, 0u, 0u);
                     st_release_u64(s, fp | SLOT_READY);
                     atomicAdd(&p.tstate->n_groups, 1ull);
                     return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
