@@ -40,15 +40,26 @@ struct TableState {
     unsigned int side_state, pad0;
 };
 
+// Context-wide counters, laid out by who touches them WHILE A LAUNCH RUNS: a load from an L2 line that atomics are queueing
+// on waits behind them (ncu, configs[2]: every CTA's prologue load of total_weight sat ~13 k cycles behind the per-warp
+// atomics on total_weight_acc next to it -- 24 % of the kernel's stall samples), so what a launch reads and what it hammers
+// never share a 128-byte line.
 struct Counters {
+    // line 0: rare atomics (bad records; every 64th tile's statistics), read by every CTA's prologue (hint)
     unsigned long long n_bad, n_nokey;
-    // FA_CFG_TOPK_ONLY: sum of the sketched weights.  total_weight is what the admission threshold of the RUNNING launch scales
-    // with (stable while it runs); the launch adds its own weights to total_weight_acc, which k_prune_* publishes afterwards.
-    unsigned long long total_weight, total_weight_acc;
     // key-repetition statistics of the two most recent submits: {lanes whose key repeats inside their warp,
     // lanes looked at}, sampled from every 64th tile.  Submit i decides from what submit i-1 saw.
     unsigned int hint[2][2];
+    unsigned long long pad0[12];
+    // line 1: FA_CFG_TOPK_ONLY: sum of the sketched weights the admission threshold of the RUNNING launch scales with --
+    // read by every CTA, written only between launches (k_publish_weight)
+    unsigned long long total_weight;
+    unsigned long long pad1[15];
+    // line 2: the running launch adds its own weights here (one atomic per warp); nothing reads it until the launch is over
+    unsigned long long total_weight_acc;
+    unsigned long long pad2[15];
 };
+static_assert(sizeof(Counters) == 384, "three 128-byte lines");
 
 struct SubmitParams {
     const uint8_t *buf;       // device bytes; buf[0] is stream byte `base`
@@ -239,12 +250,17 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const void *p)
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 // one 256-bit store (sm_100: SASS STG.E.ENL2.256): a whole, aligned 32-byte sector in a single request, so L2 has
 // nothing to merge and nothing to fetch before it can write the sector back
 __device__ __forceinline__ void st_sector(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h)
 {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
-                 : "memory");
+    const unsigned long long q0 = (unsigned long long)a | ((unsigned long long)b << 32), q1 = (unsigned long long)c | ((unsigned long long)d << 32);
+    const unsigned long long q2 = (unsigned long long)e | ((unsigned long long)f << 32), q3 = (unsigned long long)g | ((unsigned long long)h << 32);
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(q0), "l"(q1), "l"(q2), "l"(q3) : "memory");
 }
 __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
 {
@@ -282,7 +298,10 @@ __device__ __forceinline__ void side_slot_add(const SubmitParams &p, unsigned lo
     slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
 }
 
-template <int KW>
+// OUTLINE: the call sits inside a __noinline__ device function.  ptxas 12.9 narrows a 256-bit vector store to its first
+// element there (SASS: STG.E.64 instead of STG.E.ENL2.256 -- found by a failing parity test, pinned by
+// tests/test_host_logic.py::test_key_record_stores_are_whole_sectors), so that one, rare, path keeps four 16-byte stores.
+template <int KW, bool OUTLINE = false>
 __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t *key, unsigned long long h,
                                           unsigned long long bytes, unsigned long long packets, unsigned long long count)
 {
@@ -352,8 +371,15 @@ __device__ __forceinline__ void table_add(const SubmitParams &p, const uint32_t 
                 hd = atomicCAS(reinterpret_cast<unsigned long long *>(s), 0ull, fp | SLOT_BUSY);
                 if (hd == 0ull) {
                     // ours: two whole-sector stores write the key record, so L2 never has to fetch it
-                    st_sector(kr, kk[0], kk[1], kk[2], kk[3], kk[4], kk[5], kk[6], kk[7]);
-                    st_sector(kr + 32, kk[8], kk[9], kk[10], 0u, 0u, 0u, 0u, 0u);
+                    if (OUTLINE) {
+                        st_v4(kr, kk[0], kk[1], kk[2], kk[3]);
+                        st_v4(kr + 16, kk[4], kk[5], kk[6], kk[7]);
+                        st_v4(kr + 32, kk[8], kk[9], kk[10], 0u);
+                        st_v4(kr + 48, 0u, 0u, 0u, 0u);
+                    } else {
+                        st_sector(kr, kk[0], kk[1], kk[2], kk[3], kk[4], kk[5], kk[6], kk[7]);
+                        st_sector(kr + 32, kk[8], kk[9], kk[10], 0u, 0u, 0u, 0u, 0u);
+                    }
                     st_release_u64(s, fp | SLOT_READY);
                     atomicAdd(&p.tstate->n_groups, 1ull);
                     return slot_add(s + SlotLayout<KW>::VAL_OFF, bytes, packets, count);
@@ -490,6 +516,21 @@ __device__ __forceinline__ void candidate_add(const SubmitParams &p, const uint3
     }
 }
 
+// the same search continued from a first slot that has already been loaded (clo:chi = its key words)
+__device__ __forceinline__ uint8_t *candidate_find_from(const SubmitParams &p, unsigned long long klo, unsigned long long khi, uint32_t slot,
+                                                        unsigned long long clo, unsigned long long chi)
+{
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < kCandProbes; probe++) {
+        uint8_t *s = p.slots + (size_t)slot * SlotLayout<4>::BYTES;
+        if (probe) ld_relaxed_u128(s, clo, chi);
+        if (clo == klo && chi == khi) return s;
+        if ((clo & chi) == ~0ull) return nullptr;
+        slot = (slot + 1) & p.slot_mask;
+    }
+    return nullptr;
+}
+
 // the key's slot in the candidate table, or nullptr (bounded probe; an empty slot ends the search)
 __device__ __forceinline__ uint8_t *candidate_find(const SubmitParams &p, unsigned long long klo, unsigned long long khi, unsigned long long h)
 {
@@ -547,7 +588,7 @@ __device__ __forceinline__ bool hot_add_pending(uint8_t *replica, uint32_t hot_m
 // One decoded flow into the group table (+ sketch).  hot: this submit sends updates through the CTA's
 // replica first (keys repeat a lot: one shared slot per key would serialise in L2).
 // Returns the low hash bits of the key, or 0 with have=false when the flow has no key.
-template <int MODE>
+template <int MODE, bool OUTLINE = false>
 __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const Flow &f, uint32_t &nokey, bool hot, bool &have,
                                                    unsigned long long &total_w, const unsigned long long admit_bar = 0, const uint32_t rec = 0)
 {
@@ -577,13 +618,29 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         const unsigned long long w = f.bytes * f.sampling_rate;
         const unsigned long long klo = (unsigned long long)key[0] | ((unsigned long long)key[KW == 4 ? 1 : 0] << 32);
         const unsigned long long khi = (unsigned long long)key[KW == 4 ? 2 : 0] | ((unsigned long long)key[KW == 4 ? 3 : 0] << 32);
-        uint8_t *cs = (p.slots && (klo & khi) != ~0ull) ? candidate_find(p, klo, khi, h) : nullptr;
-        if (cs) {
-            // already a candidate (a heavy key): slot and sketch weight through the CTA's replica; the sketch is settled after the launch
+        // Two lookups decide a flow's path -- the CTA's replica (a key found there was a candidate when it got there, and
+        // candidates only leave between launches) and the candidate table -- and their first probes are independent loads:
+        // both are issued before either is looked at, so the common cases cost ONE L2 round trip, not two in a row.
+        const bool keyed = p.slots && (klo & khi) != ~0ull;
+        uint8_t *rep = p.hot_slots ? p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * ((size_t)p.hot_mask + 1u) * SlotLayout<4>::BYTES : nullptr;
+        uint8_t *rs = nullptr, *cs = nullptr;
+        unsigned long long rlo = 0ull, rhi = 0ull, clo = ~0ull, chi = ~0ull;
+        const uint32_t cslot = (uint32_t)(h >> 32) & p.slot_mask;
+        if (keyed) {
+            if (rep) {
+                rs = rep + (size_t)((uint32_t)(h >> 20) & p.hot_mask) * SlotLayout<4>::BYTES;
+                ld_relaxed_u128(rs, rlo, rhi);
+            }
+            ld_relaxed_u128(p.slots + (size_t)cslot * SlotLayout<4>::BYTES, clo, chi);
+        }
+        const bool in_replica = rs && rlo == klo && rhi == khi;
+        if (in_replica) {
+            slot_add_pending(rs, b, pk, 1ull, w);
+        } else if (keyed && (cs = candidate_find_from(p, klo, khi, cslot, clo, chi)) != nullptr) {
+            // a candidate (a heavy key) this replica has not met yet, or met behind a collision: slot and sketch weight through
+            // the replica when it has room; the sketch is settled after the launch
             bool done = false;
-            if (p.hot_slots)
-                done = hot_add_pending(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * ((size_t)p.hot_mask + 1u) * SlotLayout<4>::BYTES, p.hot_mask,
-                                       klo, khi, h, b, pk, w);
+            if (rep) done = hot_add_pending(rep, p.hot_mask, klo, khi, h, b, pk, w);
             if (!done) slot_add_pending(cs, b, pk, 1ull, w);
         } else {
 #ifdef FA_ADMIT_ESTIMATE
@@ -611,7 +668,7 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         bool done = false;
         if (KW <= 4 && hot)
             done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, hs, b, pk);
-        if (!done) table_add<KW>(p, key, hs, b, pk, 1ull);
+        if (!done) table_add<KW, OUTLINE>(p, key, hs, b, pk, 1ull);
     }
 #ifdef FA_CHEAP_SLOT_HASH
     if (p.cms) cms_add(p, KW > 2 ? h : hash64<KW>(key), f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
@@ -768,12 +825,13 @@ struct AggConsumer {
         const unsigned int d = __ldg(&p.counters->hint[p.hint_set ^ 1u][0]), n = __ldg(&p.counters->hint[p.hint_set ^ 1u][1]);
         return n != 0u && d * 16u >= n;  // >= 1/16 of the sampled lanes repeat
     }
+    template <bool OUTLINE = false>
     static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool hot,
                                                    Item &it)
     {
         if (ok) {
             if (!WEIGHTED) f.sampling_rate = 1;  // unused unless scale/cms, which imply WEIGHTED
-            it.h32 = aggregate_flow<MODE>(tp.p, f, nokey, hot, it.have, it.weight, it.bar, r);
+            it.h32 = aggregate_flow<MODE, OUTLINE>(tp.p, f, nokey, hot, it.have, it.weight, it.bar, r);
         } else {
             bad++;  // inserter.go:125-126: log, skip the row
         }
@@ -812,6 +870,7 @@ struct ColConsumer {
     static __device__ __forceinline__ void add_weight_one(const SubmitParams &, const Item &) {}
     static __device__ __forceinline__ unsigned long long admit_bar(const SubmitParams &) { return 0ull; }
     static __device__ __forceinline__ void set_bar(Item &, unsigned long long) {}
+    template <bool OUTLINE = false>
     static __device__ __forceinline__ void consume(const TileParams &tp, uint32_t r, bool ok, Flow &f, uint32_t &bad, uint32_t &nokey, bool, Item &)
     {
         consume(tp, r, ok, f, bad, nokey);
@@ -872,7 +931,7 @@ __device__ __noinline__ uint32_t record_from_global(const TileParams &tp, uint32
     typename Consumer::Item it;
     Consumer::item_clear(it);
     Consumer::set_bar(it, Consumer::admit_bar(tp.p));
-    Consumer::consume(tp, r, ok, f, bad, nokey, false, it);
+    Consumer::template consume<true>(tp, r, ok, f, bad, nokey, false, it);
     Consumer::add_weight_one(tp.p, it);
     return bad | (nokey << 1);
 }

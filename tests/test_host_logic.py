@@ -30,6 +30,34 @@ def test_library_carries_sm100a_code_only(fp):
     assert archs == {"sm_100a"}, archs
 
 
+def test_key_record_stores_are_whole_sectors(fp):
+    """The wide-key (5-tuple) table writes a claimed slot's 64-byte key record as two 256-bit stores -- one whole DRAM sector
+    each (SASS STG.E.ENL2.256, sm_100 only), so L2 never fetches a sector it is about to overwrite.  ptxas 12.9 silently
+    narrows such a store to its first element inside a __noinline__ device function; this pins what the shipped SASS does:
+    every claim site (the release store of the slot head is the only MEMBAR.ALL.GPU in these kernels) writes its key record
+    either as two 256-bit stores or -- the one out-of-line path -- as four 128-bit stores, never less."""
+    import subprocess
+    from collections import Counter
+
+    sass = subprocess.run(["cuobjdump", "-sass", fp.lib_path()], capture_output=True, text=True).stdout
+    fn, claims, st256, st128 = None, Counter(), Counter(), Counter()
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif "MEMBAR.ALL.GPU" in line:
+            claims[fn] += 1
+        elif "STG.E.ENL2.256" in line:
+            st256[fn] += 1
+        elif re.search(r"\bSTG\.E\.128\b", line):
+            st128[fn] += 1
+    wide = [f for f in claims if "AggConsumerILi4E" in f or "k_add_rowsILi11E" in f or "k_aggregate_columnsILi4E" in f]
+    assert len(wide) >= 10 and set(claims) == set(wide), sorted(set(claims) ^ set(wide))
+    for f in wide:
+        assert st256[f] % 2 == 0 and st128[f] % 4 == 0 and st256[f] // 2 + st128[f] // 4 == claims[f], (f, claims[f], st256[f], st128[f])
+        assert st256[f] >= 2, f                                  # the in-line (hot) site is the 256-bit one
+
+
 def test_no_gpu_means_loud_failure_not_fallback(fp):
     import torch
 
