@@ -561,7 +561,8 @@ __device__ __forceinline__ void slot_add_pending(uint8_t *s, unsigned long long 
 }
 
 __device__ __forceinline__ bool hot_add_pending(uint8_t *replica, uint32_t hot_mask, unsigned long long klo, unsigned long long khi,
-                                                unsigned long long h, unsigned long long bytes, unsigned long long packets, unsigned long long weight)
+                                                unsigned long long h, unsigned long long bytes, unsigned long long packets, unsigned long long count,
+                                                unsigned long long weight)
 {
     uint32_t slot = (uint32_t)(h >> 20) & hot_mask;
 #pragma unroll 1
@@ -577,7 +578,7 @@ __device__ __forceinline__ bool hot_add_pending(uint8_t *replica, uint32_t hot_m
             }
         }
         if (clo == klo && chi == khi) {
-            slot_add_pending(s, bytes, packets, 1ull, weight);
+            slot_add_pending(s, bytes, packets, count, weight);
             return true;
         }
         slot = (slot + 1) & hot_mask;
@@ -621,6 +622,40 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         // Two lookups decide a flow's path -- the CTA's replica (a key found there was a candidate when it got there, and
         // candidates only leave between launches) and the candidate table -- and their first probes are independent loads:
         // both are issued before either is looked at, so the common cases cost ONE L2 round trip, not two in a row.
+#ifndef FA_NO_WARP_COMBINE
+        // Heavy keys repeat inside a warp (the top address of a Zipf stream is 8 % of all flows): lanes holding the same key
+        // hand their sums to the lowest of them, which alone goes to memory -- the hottest replica sectors take a third of the
+        // atomics, and a load from a sector that atomics are queueing on waits behind them (ncu: profiles/r02).  Exact: lanes are
+        // grouped by both key halves; the sums are u64 adds in any order.
+        unsigned long long cnt = 1ull;
+        unsigned long long wsum = w;
+        {
+            const unsigned act = __activemask();
+            const unsigned lane = threadIdx.x & 31u;
+            const unsigned peers = __match_any_sync(act, klo) & __match_any_sync(act, khi);
+            const unsigned others = peers & ~(1u << lane);
+            const int rounds = __reduce_max_sync(act, (unsigned)__popc(others));
+            const unsigned long long b0 = b, pk0 = pk, w0 = w;
+            unsigned rest = others;
+            for (int i = 0; i < rounds; i++) {
+                const int src = rest ? __ffs((int)rest) - 1 : (int)lane;
+                const unsigned long long ob = __shfl_sync(act, b0, src), opk = __shfl_sync(act, pk0, src), ow = __shfl_sync(act, w0, src);
+                if (rest) {
+                    b += ob;
+                    pk += opk;
+                    wsum += ow;
+                    cnt++;
+                    rest &= rest - 1u;
+                }
+            }
+            if ((peers & ((1u << lane) - 1u)) != 0u) {  // a lower lane carries this key: nothing left to do here
+                total_w += w;
+                return (uint32_t)h;
+            }
+        }
+#else
+        const unsigned long long cnt = 1ull, wsum = w;
+#endif
         const bool keyed = p.slots && (klo & khi) != ~0ull;
         uint8_t *rep = p.hot_slots ? p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * ((size_t)p.hot_mask + 1u) * SlotLayout<4>::BYTES : nullptr;
         uint8_t *rs = nullptr, *cs = nullptr;
@@ -635,30 +670,30 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         }
         const bool in_replica = rs && rlo == klo && rhi == khi;
         if (in_replica) {
-            slot_add_pending(rs, b, pk, 1ull, w);
+            slot_add_pending(rs, b, pk, cnt, wsum);
         } else if (keyed && (cs = candidate_find_from(p, klo, khi, cslot, clo, chi)) != nullptr) {
             // a candidate (a heavy key) this replica has not met yet, or met behind a collision: slot and sketch weight through
             // the replica when it has room; the sketch is settled after the launch
             bool done = false;
-            if (rep) done = hot_add_pending(rep, p.hot_mask, klo, khi, h, b, pk, w);
-            if (!done) slot_add_pending(cs, b, pk, 1ull, w);
+            if (rep) done = hot_add_pending(rep, p.hot_mask, klo, khi, h, b, pk, cnt, wsum);
+            if (!done) slot_add_pending(cs, b, pk, cnt, wsum);
         } else {
 #ifdef FA_ADMIT_ESTIMATE
             // round-2 first version: admit on the estimate the update itself returns (four RETURNING atomics per flow)
-            const unsigned long long est = cms_add_estimate(p, h, w);
-            if (p.slots && est >= admit_bar) candidate_add(p, key, h, b, pk, 1ull);
+            const unsigned long long est = cms_add_estimate(p, h, wsum);
+            if (p.slots && est >= admit_bar) candidate_add(p, key, h, b, pk, cnt);
 #else
             // sample and hold (Estan & Varghese): the sketch takes the flow through fire-and-forget reductions, and the flow
             // makes its key a candidate with probability min(1, w / bar), bar = total weight / (64 K) -- at most 64 K
             // admissions are expected per launch whatever the number of keys, and a key that weighs several bars (every
             // top-K key does) is admitted with probability 1 - exp(-weight / bar).  The draw is a hash of (key, record
             // number, submit number): the same stream admits the same keys on every run.
-            cms_add(p, h, w);
+            cms_add(p, h, wsum);
             uint32_t u = (uint32_t)(h >> 11) ^ (rec * 0x9E3779B9u) ^ p.sample_seed;
             u ^= u >> 16; u *= 0x7FEB352Du; u ^= u >> 15; u *= 0x846CA68Bu; u ^= u >> 16;
             const unsigned long long lo = (unsigned long long)u * admit_bar, hi = __umul64hi((unsigned long long)u, admit_bar);
-            const bool admit = w >= admit_bar || hi < (w >> 32) || (hi == (w >> 32) && lo < (w << 32));   // u / 2^32 < w / bar
-            if (p.slots && admit) candidate_add(p, key, h, b, pk, 1ull);
+            const bool admit = wsum >= admit_bar || hi < (wsum >> 32) || (hi == (wsum >> 32) && lo < (wsum << 32));   // u / 2^32 < w / bar
+            if (p.slots && admit) candidate_add(p, key, h, b, pk, cnt);
 #endif
         }
         total_w += w;
@@ -783,7 +818,12 @@ struct AggConsumer {
 #ifndef FA_AGG_MIN_BLOCKS
 #define FA_AGG_MIN_BLOCKS 8
 #endif
-    static constexpr int MIN_BLOCKS = KW <= 4 ? FA_AGG_MIN_BLOCKS : 5;  // 32 / 48 registers per thread
+#ifndef FA_AGG_MIN_BLOCKS_W4
+#define FA_AGG_MIN_BLOCKS_W4 6
+#endif
+    // 32 registers per thread (8 CTAs per SM) for the roll-ups; 40 for weighted address keys (sketch + candidate paths: at 32 the
+    // warp-combining loop spills 350 bytes per thread); 48 for the 5-tuple
+    static constexpr int MIN_BLOCKS = KW <= 2 ? FA_AGG_MIN_BLOCKS : (KW == 4 ? (WEIGHTED ? FA_AGG_MIN_BLOCKS_W4 : FA_AGG_MIN_BLOCKS) : 5);
     static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     static constexpr bool PERMUTE = true;                // nothing is stored per record: lanes may take any record
     struct Item {

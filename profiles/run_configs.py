@@ -104,12 +104,14 @@ def topk_bounded(a):
     return res
 
 
-if want("configs[2]"):
+N2 = int(os.environ.get("FA_CONFIG2_FLOWS", 1_000_000_000))
+if want("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, EXACT"):
     with fp.FlowAgg("srcaddr", stream=stream, cms=True, cms_depth=4, cms_width_log2=20, table_capacity=1 << 25) as a:
-        run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, EXACT candidate table (1.6 GB, every key)", a, cfg, 1_000_000_000, topk_exact)
+        run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, EXACT candidate table (1.6 GB, every key)", a, cfg, N2, topk_exact)
+if want("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, bounded"):
     # the sketch workload proper: bounded candidate set (FA_CFG_TOPK_ONLY), memory independent of the number of keys
     with fp.FlowAgg("srcaddr", stream=stream, topk_only=True, topk_k=1000, cms_depth=4, cms_width_log2=20) as a:
-        run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, bounded candidates (FA_CFG_TOPK_ONLY, 12 MiB table)", a, cfg, 1_000_000_000, topk_bounded)
+        run("configs[2] CMS d=4 w=2^20 top-1000 SrcAddr over 1B flows, bounded candidates (FA_CFG_TOPK_ONLY, 12 MiB table)", a, cfg, N2, topk_bounded)
 # configs[4]: 100M unique 5-tuples, HBM open-address table at load 0.37
 cfg = fp.FaMockerConfig.make(seed=1, flows_per_second=250_000, addr_mode=2, framed=True)
 if want("configs[4]"):
