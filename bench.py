@@ -35,14 +35,15 @@ sys.path.insert(0, ROOT)
 
 N_FLOWS = 100_000_000
 SLAB = 1 << 24
-TABLE_CAP = 1 << 19  # 65 536 groups at load 1/8: 16 MiB of 32-byte slots, L2-resident
+# 65 536 groups at load 1/8: 16 MiB of 32-byte slots, L2-resident (FA_BENCH_TABLE_CAP: experiments with the probe length only)
+TABLE_CAP = int(os.environ.get("FA_BENCH_TABLE_CAP", 1 << 19))
 WORKLOAD = "configs[1]: 100M mocker FlowMessages, (SrcAS,DstAS) group-by sum(Bytes,Packets), 64k unique AS pairs"
 METRIC = "flows/sec aggregated (decode+aggregate); achieved HBM GB/s vs peak"
 
 
 def bench_config():
     """The workload's name tag, identical for both arms (the driver compares the two lines' config)."""
-    return {"workload": WORKLOAD, "flows_per_step_per_gpu": N_FLOWS, "key": "(SrcAS,DstAS)", "groups": 65536,
+    return {"workload": WORKLOAD, "flows_per_step_per_gpu": N_FLOWS, "key": "(SrcAS,DstAS)", "groups": 65536, "table_slots": TABLE_CAP,
             "partitioning": "kafka partition = rank, one mocker instance (own seed, SequenceNum from 0) per partition"}
 
 

@@ -622,7 +622,8 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         // Two lookups decide a flow's path -- the CTA's replica (a key found there was a candidate when it got there, and
         // candidates only leave between launches) and the candidate table -- and their first probes are independent loads:
         // both are issued before either is looked at, so the common cases cost ONE L2 round trip, not two in a row.
-#ifndef FA_NO_WARP_COMBINE
+#ifdef FA_WARP_COMBINE
+        // (experiment, off: measured 1.5 % SLOWER on configs[2], profiles/r02/experiments)
         // Heavy keys repeat inside a warp (the top address of a Zipf stream is 8 % of all flows): lanes holding the same key
         // hand their sums to the lowest of them, which alone goes to memory -- the hottest replica sectors take a third of the
         // atomics, and a load from a sector that atomics are queueing on waits behind them (ncu: profiles/r02).  Exact: lanes are
@@ -819,10 +820,11 @@ struct AggConsumer {
 #define FA_AGG_MIN_BLOCKS 8
 #endif
 #ifndef FA_AGG_MIN_BLOCKS_W4
-#define FA_AGG_MIN_BLOCKS_W4 6
+#define FA_AGG_MIN_BLOCKS_W4 5
 #endif
-    // 32 registers per thread (8 CTAs per SM) for the roll-ups; 40 for weighted address keys (sketch + candidate paths: at 32 the
-    // warp-combining loop spills 350 bytes per thread); 48 for the 5-tuple
+    // 32 registers per thread (8 CTAs per SM) for the roll-ups; 48 (5 CTAs) for weighted address keys -- sketch + candidate paths
+    // are bound by L2 latency, not by issue slots, and measured 1.92 / 1.76 / 1.69 ms per slab at 32 / 40 / 48 registers -- and for
+    // the 5-tuple
     static constexpr int MIN_BLOCKS = KW <= 2 ? FA_AGG_MIN_BLOCKS : (KW == 4 ? (WEIGHTED ? FA_AGG_MIN_BLOCKS_W4 : FA_AGG_MIN_BLOCKS) : 5);
     static constexpr bool HOT = KW <= 4;                 // 5-tuples are high-cardinality by nature
     static constexpr bool PERMUTE = true;                // nothing is stored per record: lanes may take any record
