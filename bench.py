@@ -557,8 +557,57 @@ def main():
             ems = float(t.item())
         e2e = {"value": world * n_flows * args.steps / (ems * 1e-3), "unit": "flows/s",
                "h2d_bytes_per_step": int(in_bytes + 4 * (n_flows + len(slabs))), "d2h_bytes_per_step": int(rows.nbytes),
-               "ms_per_step": ems / args.steps,
+               "ms_per_step": ems / args.steps, "input": "records + host offsets",
                "note": "pinned host buffers -> fa_submit (64 MiB batches, copy/compute overlapped) -> fa_flush_begin/_end rows into a host array"}
+
+        # ---- the same, WITHOUT shipping offsets: the host only cuts the stream into <= 64 MiB pieces at message boundaries (it knows
+        # them: it concatenated the Kafka values) and fa_submit(offsets = NULL) finds the records on the GPU.  The link is the limit
+        # of this leg, so the 4 bytes per flow that do not cross it are throughput.
+        if not args.no_frame_leg:
+            pieces = []
+            for (hb, ho, n, nb) in hslabs:
+                o = ho.numpy().astype(np.int64)
+                r0 = 0
+                while r0 < n:
+                    r1 = int(np.searchsorted(o, o[r0] + (64 << 20), side="right")) - 1
+                    r1 = min(max(r1, r0 + 1), n)
+                    pieces.append((hb[int(o[r0]):int(o[r1])], int(o[r1] - o[r0])))
+                    r0 = r1
+
+            def step_e2e_framed():
+                for (piece, nbytes) in pieces:
+                    eagg.submit(piece, None, framed=True, nbytes=nbytes)
+                rows_prev = collect(eagg)
+                eagg.flush_begin()
+                pending[0] = True
+                return rows_prev
+
+            check_rows(collect(eagg))                      # nothing pending from the leg above
+            for _ in range(max(1, args.warmup - 1)):
+                check_rows(step_e2e_framed())
+            assert np.array_equal(collect(eagg), rows), "offsets found on the GPU (host submit) give other rows"
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                check_rows(step_e2e_framed())
+            grows = collect(eagg)
+            g1.record()
+            barrier()
+            assert np.array_equal(grows, rows)
+            gms = g0.elapsed_time(g1)
+            if world > 1:
+                t = torch.tensor([gms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                gms = float(t.item())
+            e2e_framed = {"value": world * n_flows * args.steps / (gms * 1e-3), "unit": "flows/s", "h2d_bytes_per_step": int(in_bytes),
+                          "d2h_bytes_per_step": int(rows.nbytes), "ms_per_step": gms / args.steps, "input": "records only (offsets found on the GPU)",
+                          "submits_per_step": len(pieces),
+                          "note": "pinned host buffers -> fa_submit(offsets = NULL) per <= 64 MiB piece (index + launch run one call behind, "
+                                  "overlapping the next piece's copy) -> fa_flush_begin/_end rows into a host array"}
+            if e2e_framed["value"] > e2e["value"]:   # same metric, same API, same host buffers: the better of the two ways to hand them over
+                e2e, e2e_framed = e2e_framed, e2e
+            e2e["other_input"] = e2e_framed
         eagg.close()
         del hslabs
 

@@ -41,6 +41,13 @@ struct fa_ctx {
     uint64_t capacity = 0;
     bool weighted = false;
     uint32_t admit_shift = 0;  // FA_CFG_TOPK_ONLY: log2(64 * topk_k), 0 otherwise
+    // offsets-free host submits run one call behind: the batch staged by the latest fa_submit(offsets = NULL) is indexed
+    // and launched by the NEXT call (or by whatever reads the context), so that the one host look the index needs waits
+    // while the next batch's host-to-device copy is already running
+    bool frame_pending = false;
+    int frame_stage = 0;
+    size_t frame_len = 0;
+    uint32_t frame_flags = 0;
     uint32_t hot_slots_per_replica = kHotSlots;
 
     cudaStream_t stream = nullptr;  // compute
@@ -616,12 +623,33 @@ extern "C" int fa_host_buffer(fa_ctx *c, int slot, uint8_t **buf, size_t *cap_by
     return FA_OK;
 }
 
+// index and launch the offsets-free batch the previous fa_submit staged (no-op when there is none)
+static int finish_frame(fa_ctx *c)
+{
+    if (!c->frame_pending) return FA_OK;
+    c->frame_pending = false;
+    FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    const int i = c->frame_stage;
+    FA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_staged[i], 0));
+    uint32_t n_found = 0;
+    int rc = frame_index_device(c, c->d_stage[i], c->frame_len, &n_found);
+    if (rc == FA_OK) rc = launch_batch(c, c->d_stage[i], 0, c->frame_len, c->d_frame_off, n_found, c->frame_flags);
+    cudaEventRecord(c->ev_consumed[i], c->stream);  // the stage is free again whatever happened to its batch
+    return rc;
+}
+#define FA_DRAIN(c)                      \
+    do {                                 \
+        const int rc_ = finish_frame(c); \
+        if (rc_) return rc_;             \
+    } while (0)
+
 extern "C" int fa_submit_device(fa_ctx *c, const uint8_t *d_buf, size_t len, const uint32_t *d_offsets, uint32_t n_records,
                                 uint32_t flags)
 {
     if (!c || (!d_buf && len)) return FA_ERR_INVALID;
     if (((uintptr_t)d_buf & 15u) || len > 0xFFFFFFF0ull) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     if (!d_offsets) {
         if (!(flags & FA_FRAMED)) return FA_ERR_INVALID;
         uint32_t n_found = 0;
@@ -653,15 +681,16 @@ extern "C" int fa_submit(fa_ctx *c, const uint8_t *buf, size_t len, const uint32
         for (int s = 0; s < 2; s++)
             if (buf >= c->h_slab[s] && c->h_slab[s] && buf < c->h_slab[s] + c->cfg.max_batch_bytes)
                 FA_CUDA(c, cudaEventRecord(c->ev_slab[s], c->copy_stream));
-        FA_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_staged[i], 0));
-        uint32_t n_found = 0;
-        rc = frame_index_device(c, c->d_stage[i], len, &n_found);
-        if (rc) return rc;
+        // the previous offsets-free batch (the other stage): its index's host look overlaps the copy just enqueued
+        rc = finish_frame(c);
+        c->frame_pending = true;
+        c->frame_stage = i;
+        c->frame_len = len;
+        c->frame_flags = flags;
         c->bytes_in += len;
-        rc = launch_batch(c, c->d_stage[i], 0, len, c->d_frame_off, n_found, flags);
-        FA_CUDA(c, cudaEventRecord(c->ev_consumed[i], c->stream));
         return rc;
     }
+    FA_DRAIN(c);
     if (n_records == 0) return FA_OK;
     // cut into batches at record boundaries; copy of batch i+1 overlaps kernel of batch i
     uint32_t r0 = 0;
@@ -720,6 +749,7 @@ extern "C" int fa_sync(fa_ctx *c)
 {
     if (!c) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     FA_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     FA_CUDA(c, cudaStreamSynchronize(c->stream));
     return FA_OK;
@@ -995,6 +1025,7 @@ extern "C" int fa_flush_begin(fa_ctx *c, uint32_t flags)
 {
     if (!c || !c->d_slots || c->flush_pending) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     c->flush_flags = flags;
     if ((flags & (FA_FLUSH_KEEP | FA_FLUSH_UNSORTED)) || !flush_async_ok(c)) {
         // peeks, unsorted dumps and huge tables are drained by fa_flush_end itself, in place
@@ -1088,6 +1119,7 @@ extern "C" int fa_flush_end(fa_ctx *c, fa_row *rows, size_t cap, size_t *n)
     if (!c || !n || !c->flush_pending) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
     if (c->flush_deferred) {
+        FA_DRAIN(c);
         const int rc = flush_sync(c, rows, cap, n, c->flush_flags);
         if (rc != FA_ERR_CAPACITY) c->flush_pending = c->flush_deferred = false;
         return rc;
@@ -1126,6 +1158,7 @@ extern "C" int fa_flush_end(fa_ctx *c, fa_row *rows, size_t cap, size_t *n)
 extern "C" int fa_flush(fa_ctx *c, fa_row *rows, size_t cap, size_t *n, uint32_t flags)
 {
     if (!c || !n || !c->d_slots || c->flush_pending) return FA_ERR_INVALID;
+    FA_DRAIN(c);
     return flush_sync(c, rows, cap, n, flags);
 }
 
@@ -1246,6 +1279,7 @@ extern "C" int fa_merge_rows(fa_ctx *c, const fa_row *rows, size_t n, uint32_t o
     if (!c || !c->d_slots || (n && !rows) || (n_owners > 1 && owner >= n_owners)) return FA_ERR_INVALID;
     if (!n) return FA_OK;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     cudaPointerAttributes attr{};
     const bool on_device = cudaPointerGetAttributes(&attr, rows) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();
@@ -1326,6 +1360,7 @@ extern "C" int fa_flush_box(fa_ctx *const *ctxs, int n_ctx, fa_row *rows, size_t
     for (int i = 0; i < n_ctx; i++)
         if (!ctxs[i] || !ctxs[i]->d_slots || ctxs[i]->cfg.key_mode != ctxs[0]->cfg.key_mode || ctxs[i]->flush_pending) return FA_ERR_INVALID;
     if (n_ctx == 1) return fa_flush(ctxs[0], rows, cap, n, flags);
+    for (int i = 0; i < n_ctx; i++) FA_DRAIN(ctxs[i]);
     // 1. every context: fold the replicas, compact its rows (unsorted) into its scratch block, empty its table
     std::vector<uint64_t> groups(n_ctx, 0);
     uint64_t dropped = 0;
@@ -1440,6 +1475,7 @@ extern "C" int fa_cms_device(fa_ctx *c, int which, void **d_ptr, size_t *n_words
 {
     if (!c || !d_ptr || !c->d_cms) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     if (which == FA_CMS_GLOBAL) {
         int rc = ensure_cms_global(c);
         if (rc) return rc;
@@ -1690,6 +1726,7 @@ extern "C" int fa_topk(fa_ctx *const *ctxs, int n_ctx, size_t k, fa_hh *out, siz
 extern "C" int fa_columns(fa_ctx *c, fa_columns_view *v)
 {
     if (!c || !v || !(c->cfg.flags & FA_CFG_COLUMNS)) return FA_ERR_INVALID;
+    FA_DRAIN(c);
     const Columns &k = c->cols;
     v->n_records = c->cols_n;
     v->valid = k.valid;
@@ -1718,6 +1755,7 @@ extern "C" int fa_columns(fa_ctx *c, fa_columns_view *v)
 extern "C" int fa_columns_read(fa_ctx *c, const char *col, void *out, size_t cap_bytes)
 {
     if (!c || !col || !out || !(c->cfg.flags & FA_CFG_COLUMNS)) return FA_ERR_INVALID;
+    FA_DRAIN(c);
     const Columns &k = c->cols;
     struct Ent { const char *name; const void *ptr; size_t elem; };
     const Ent ents[] = {
@@ -1748,6 +1786,7 @@ extern "C" int fa_timer_start(fa_ctx *c)
 {
     if (!c) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     FA_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
     return FA_OK;
 }
@@ -1756,6 +1795,7 @@ extern "C" int fa_timer_stop(fa_ctx *c, float *ms)
 {
     if (!c || !ms) return FA_ERR_INVALID;
     FA_CUDA(c, cudaSetDevice(c->cfg.device));
+    FA_DRAIN(c);
     FA_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
     FA_CUDA(c, cudaEventSynchronize(c->ev_t1));
     FA_CUDA(c, cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));

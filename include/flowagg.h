@@ -162,7 +162,15 @@ int fa_host_buffer(fa_ctx *ctx, int slot, uint8_t **buf, size_t *cap_bytes, uint
  * max_batch_records are cut into batches at record boundaries and pipelined
  * (copy of batch i+1 overlaps the kernel of batch i).  Asynchronous; the host
  * buffers may be reused after fa_sync, or -- for the library's slabs -- after
- * fa_host_buffer returns them again. */
+ * fa_host_buffer returns them again.
+ * offsets == NULL: len <= max_batch_bytes, the stream must start and end on a
+ * record boundary, and the call runs ONE BEHIND: it enqueues this batch's
+ * host-to-device copy and then indexes and launches the batch the previous such
+ * call staged (the index needs one host look at three device counters, which now
+ * waits while the next copy is already running).  Whatever reads the context
+ * (fa_sync, fa_flush*, fa_stats_get, fa_topk*, ...) first finishes the batch
+ * still pending; an error of a deferred batch is reported by the call that
+ * finishes it. */
 int fa_submit(fa_ctx *ctx, const uint8_t *buf, size_t len, const uint32_t *offsets, uint32_t n_records,
               uint32_t flags);
 

@@ -8,7 +8,19 @@ timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.l
 tail -2 gpurun_out/${TAG}_pytest_gpu.log
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
-cut -c1-700 gpurun_out/${TAG}_bench.json
+if [ ! -s gpurun_out/${TAG}_bench.json ]; then
+  tail -5 gpurun_out/${TAG}_bench.err
+  timeout 900 python bench.py --steps 10 --warmup 3 --no-frame-leg > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench_noframe.err
+fi
+python - <<PY
+import json
+d=json.load(open("gpurun_out/${TAG}_bench.json"))
+print("value %.4g ms/step %.3f kernel %.4f ms frac %.3f"%(d["value"],d["ms_per_step"],d["roofline"]["avg_launch_ms"],d["roofline"]["frac"]))
+e=d["e2e"]; print("e2e %.4g (%s) ms/step %.2f"%(e["value"],e.get("input"),e["ms_per_step"]))
+o=e.get("other_input"); 
+if o: print("other e2e %.4g (%s) ms/step %.2f"%(o["value"],o.get("input"),o["ms_per_step"]))
+print("cpu", d["cpu_baseline"]["value"], "framed_stream", d.get("framed_stream",{}).get("ms_per_slab"))
+PY
 for cap in 1048576 2097152; do
   FA_BENCH_TABLE_CAP=$cap timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-frame-leg > gpurun_out/${TAG}_bench_cap${cap}.json 2> gpurun_out/${TAG}_bench_cap${cap}.err
   python -c "

@@ -281,6 +281,35 @@ def test_null_offsets_framing_on_gpu(fp, oracle, fuzz_2k, torch_cuda):
         assert st["n_records"] == 40000 and st["n_bad"] == 1
 
 
+def test_offsets_free_host_submits_run_one_behind(fp, oracle, torch_cuda):
+    """fa_submit(offsets = NULL) stages its batch and finishes the previous one (include/flowagg.h): a run of such submits, a
+    with-offsets submit in between, and every reader of the context (stats, flush_begin/_end, flush) must see exactly the
+    records submitted so far -- rows == oracle over the whole stream, whatever call finished which batch."""
+    cfg = fp.FaMockerConfig.make(seed=41, flows_per_second=1000, n_src_as=64, n_dst_as=64, framed=True)
+    parts = [fp.mocker_host(cfg, i * 30000, 30000) for i in range(5)]
+    blob = np.concatenate([b for b, _ in parts])
+    offs = np.concatenate([[0]] + [o[1:].astype(np.int64) + sum(len(bb) for bb, _ in parts[:i]) for i, (_, o) in enumerate(parts)]).astype(np.uint32)
+    want, _, res = oracle.run_batch(blob, offs, framed=True, key_mode="aspair")
+    with fp.FlowAgg("aspair", max_batch_bytes=4 << 20) as a:
+        a.submit(parts[0][0], None, framed=True)               # staged only
+        a.submit(parts[1][0], None, framed=True)               # finishes 0, stages 1
+        assert a.stats()["n_records"] == 60000                 # a reader finishes 1
+        a.submit(parts[2][0], None, framed=True)               # staged
+        a.submit(*parts[3], framed=True)                       # a with-offsets submit finishes 2 first, then runs
+        a.submit(parts[4][0], None, framed=True)               # staged
+        a.flush_begin()                                        # finishes 4 before the tables swap
+        rows = a.flush_end()
+        assert np.array_equal(rows, want)
+        assert a.stats()["n_records"] == 150000 and a.stats()["n_bad"] == 0
+        # a window of its own after the swap, closed by the synchronous flush
+        a.submit(parts[0][0], None, framed=True)
+        w0, _, _ = oracle.run_batch(*parts[0], framed=True, key_mode="aspair")
+        assert np.array_equal(a.flush(), w0)
+        # a piece larger than max_batch_bytes is refused, not truncated
+        with pytest.raises(fp.FlowAggError):
+            a.submit(blob, None, framed=True)
+
+
 def test_table_full_is_reported_not_silent(fp, torch_cuda):
     cfg = fp.FaMockerConfig.make(seed=12, flows_per_second=10, addr_mode=2, framed=True)
     buf, offs = fp.mocker_host(cfg, 0, 5000)
