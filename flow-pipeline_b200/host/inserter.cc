@@ -69,6 +69,8 @@ struct Flags {
                                           //       14-column row per flow (inserter.go:51-66,142-157), TSV as Go would print it;
                                           //       copy: the same rows as a Postgres `COPY flows (...) FROM stdin` script
     bool FlushBox = false;                // -flush.box: the closing flush is ONE exact roll-up over every partition (fa_flush_box)
+    bool OffsetsOnGPU = false;            // -offsets.gpu: hand the slab over WITHOUT its offsets array (fa_submit(offsets = NULL)): the library
+                                          //       finds the record boundaries on the GPU; 4 bytes per flow less over PCIe
     bool DryRun = false;                  // -dry-run: walk the claims and fill slabs, no GPU, no aggregates
     bool Metrics = false;                 // -metrics: serve -metrics.addr (off by default in this mirror)
     double Linger = 0;                    // -linger: keep serving metrics this long after the claims are drained (or until SIGTERM)
@@ -134,6 +136,7 @@ static bool parse_flags(int argc, char **argv, Flags &f)
         else if (a == "gpus") f.Devices = atoi(val().c_str());
         else if (a == "dry-run") f.DryRun = true;
         else if (a == "flush.box") f.FlushBox = true;
+        else if (a == "offsets.gpu") f.OffsetsOnGPU = true;
         else if (a == "metrics") f.Metrics = true;
         else if (a == "linger") f.Linger = parse_duration(val());
         else {
@@ -366,7 +369,10 @@ struct state {
     {
         if (ps.nrec == 0) return;
         if (!fl.DryRun) {
-            int rc = fa_submit(ps.ctx, ps.slab, ps.fill, ps.offs, (uint32_t)ps.nrec, FA_FRAMED);
+            // per-flow sinks read the decoded columns of THIS slab right after the submit: they keep the offsets (and the
+            // synchronous hand-over); the roll-up sinks may run one slab behind (include/flowagg.h)
+            const bool no_offsets = fl.OffsetsOnGPU && !per_flow_sink();
+            int rc = fa_submit(ps.ctx, ps.slab, ps.fill, no_offsets ? nullptr : ps.offs, (uint32_t)ps.nrec, FA_FRAMED);
             if (rc) {
                 logf(0, "fa_submit: %s (%s)", fa_strerror(rc), fa_last_error(ps.ctx));
                 exit(1);

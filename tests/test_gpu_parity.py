@@ -445,6 +445,12 @@ def test_host_inserter_mirror_rows_equal_oracle(fp, oracle, torch_cuda, tmp_path
     want2 = [(time.strftime("%Y-%m-%d %H:%M:%S", time.gmtime(int(w["key"][0]))), str(w["key"][1]), str(w["key"][2]), f"[{w['key'][3]}]",
               str(w["bytes"]), str(w["packets"]), str(w["count"])) for w in merged]
     assert got2 == want2
+    # -offsets.gpu: the slabs go to the library without their offsets (boundaries found on the GPU, one slab behind): same rows
+    out2b = tmp_path / "rows_box_nooff.tsv"
+    r = subprocess.run([exe, "-claim.file", ",".join(files), "-flush.count", "0", "-flush.dur", "1h", "-flush.box", "-offsets.gpu", "-out", str(out2b)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out2b.read_text() == out2.read_text()
     # -format rowbinary: what `INSERT INTO flows_5m FORMAT RowBinary` takes (create.sh:70-87), 70 bytes per row
     out3 = tmp_path / "rows_box.bin"
     r = subprocess.run([exe, "-claim.file", ",".join(files), "-flush.count", "0", "-flush.dur", "1h", "-flush.box", "-format", "rowbinary",
