@@ -80,31 +80,17 @@ __device__ __forceinline__ unsigned long long frame_next(const uint8_t *buf, uns
     return body + v;
 }
 
-// Byte readers for the speculation: straight from global memory, or through a window of the stream that the warp has
-// staged in shared memory (positions outside the window fall back to global loads: big records, the stream's tail).
-struct GlobalBytes {
-    const uint8_t *buf;
-    __device__ __forceinline__ uint32_t operator()(unsigned long long p) const { return __ldg(buf + p); }
-};
-struct WindowBytes {
-    const uint8_t *buf;
-    const uint8_t *win;           // shared memory
-    unsigned long long w0, w1;    // the window holds stream bytes [w0, w1)
-    __device__ __forceinline__ uint32_t operator()(unsigned long long p) const { return (p >= w0 && p < w1) ? win[p - w0] : __ldg(buf + p); }
-};
-
 // <= 2-byte varint at p (p < end).  n = bytes taken, 0 if it is longer or cut off.
-template <class Rd>
-__device__ __forceinline__ uint32_t frame_varint2(const Rd rd, unsigned long long p, unsigned long long end, uint32_t &n)
+__device__ __forceinline__ uint32_t frame_varint2(const uint8_t *buf, unsigned long long p, unsigned long long end, uint32_t &n)
 {
-    const uint32_t b0 = rd(p);
+    const uint32_t b0 = __ldg(buf + p);
     if (b0 < 0x80u) {
         n = 1;
         return b0;
     }
     n = 0;
     if (p + 1 >= end) return 0;
-    const uint32_t b1 = rd(p + 1);
+    const uint32_t b1 = __ldg(buf + p + 1);
     if (b1 >= 0x80u) return 0;
     n = 2;
     return (b0 & 0x7fu) | (b1 << 7);
@@ -112,12 +98,11 @@ __device__ __forceinline__ uint32_t frame_varint2(const Rd rd, unsigned long lon
 
 // Does a plausible record start at p?  varint(len) with len >= 2, then fields with ascending numbers whose values chain
 // exactly to p + header + len.  Returns the position behind the record, or 0.  A heuristic for the speculation only.
-template <class Rd>
-__device__ __forceinline__ unsigned long long frame_plausible_record(const Rd rd, unsigned long long p, unsigned long long len)
+__device__ __forceinline__ unsigned long long frame_plausible_record(const uint8_t *buf, unsigned long long p, unsigned long long len)
 {
     if (p >= len) return 0;
     uint32_t hn;
-    const uint32_t ln = frame_varint2(rd, p, len, hn);
+    const uint32_t ln = frame_varint2(buf, p, len, hn);
     if (!hn || ln < 2u) return 0;
     unsigned long long q = p + hn;
     const unsigned long long end = q + ln;
@@ -125,7 +110,7 @@ __device__ __forceinline__ unsigned long long frame_plausible_record(const Rd rd
     uint32_t last = 0;
     while (q < end) {
         uint32_t tn;
-        const uint32_t tag = frame_varint2(rd, q, end, tn);
+        const uint32_t tag = frame_varint2(buf, q, end, tn);
         if (!tn) return 0;
         q += tn;
         const uint32_t num = tag >> 3, wt = tag & 7u;
@@ -135,13 +120,13 @@ __device__ __forceinline__ unsigned long long frame_plausible_record(const Rd rd
             uint32_t k = 0;
             for (;; k++) {
                 if (q + k >= end || k >= 10u) return 0;
-                if (rd(q + k) < 0x80u) break;
+                if (__ldg(buf + q + k) < 0x80u) break;
             }
             q += k + 1u;
         } else if (wt == 2u) {
             if (q >= end) return 0;
             uint32_t vn;
-            const uint32_t v = frame_varint2(rd, q, end, vn);
+            const uint32_t v = frame_varint2(buf, q, end, vn);
             if (!vn) return 0;
             q += vn + v;
         } else if (wt == 1u) {
@@ -156,40 +141,22 @@ __device__ __forceinline__ unsigned long long frame_plausible_record(const Rd rd
     return end;
 }
 
-constexpr uint32_t kFrameWindow = 1024;  // bytes behind a tile's start staged per warp: 256 candidate positions + three mocker-sized records
-
-// One warp per tile, 8 tiles per block.  The warp first copies the head of its tile into shared memory with two coalesced
-// 16-byte loads per lane; the candidates are then parsed from there (a candidate is ~40 dependent byte reads: from global
-// memory they were the whole cost of this kernel, 0.44 ms per 1.4 GB).
-__global__ void __launch_bounds__(256) k_frame_speculate(const uint8_t *buf, unsigned long long len, uint32_t n_tiles, uint32_t *entry, uint8_t *dirty)
+__global__ void k_frame_speculate(const uint8_t *buf, unsigned long long len, uint32_t n_tiles, uint32_t *entry, uint8_t *dirty)
 {
-    __shared__ __align__(16) uint8_t win[8][kFrameWindow];
     const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (tile >= n_tiles) return;  // whole warps leave together
+    const uint32_t lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
     const unsigned long long start = (unsigned long long)tile * kFrameTile;
-    const unsigned long long readable = (len + 15ull) & ~15ull;  // include/flowagg.h: the buffer is readable up to len rounded up to 16
     uint32_t best = 0xFFFFFFFFu;
     if (tile == 0) {
         best = 0;
     } else {
-        for (uint32_t i = lane; i < kFrameWindow / 16u; i += 32u) {
-            const unsigned long long at = start + 16ull * i;
-            const uint4 v = at < readable ? __ldg(reinterpret_cast<const uint4 *>(buf + at)) : make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4 *>(&win[w][16u * i]) = v;
-        }
-        __syncwarp();
-        WindowBytes rd;
-        rd.buf = buf;
-        rd.win = win[w];
-        rd.w0 = start;
-        rd.w1 = min(start + (unsigned long long)kFrameWindow, len);
         for (uint32_t j = 0; j < kFrameSearch / 32u && best == 0xFFFFFFFFu; j++) {
             unsigned long long p = start + j * 32u + lane;
             const unsigned long long cand = p;
             bool ok = true;
             for (uint32_t k = 0; k < kFrameConfirm && ok && p < len; k++) {
-                p = frame_plausible_record(rd, p, len);
+                p = frame_plausible_record(buf, p, len);
                 ok = p != 0;
             }
             ok = ok && cand < len;
@@ -204,16 +171,6 @@ __global__ void __launch_bounds__(256) k_frame_speculate(const uint8_t *buf, uns
     }
 }
 
-// The walks hop from length prefix to length prefix: one dependent load per record, ~190 per tile, each a DRAM round trip
-// on a stream nobody has touched yet.  Every hop therefore asks L2 for the line a dozen records ahead (hops advance less than
-// a line, so every line of the tile gets asked for once): the chain then runs at L2 latency.
-constexpr unsigned long long kFrameAhead = 1024;
-__device__ __forceinline__ void frame_prefetch(const uint8_t *buf, unsigned long long pos, unsigned long long len)
-{
-    const unsigned long long at = pos + kFrameAhead;
-    if (at < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(buf + at));
-}
-
 __global__ void k_frame_walk(const uint8_t *buf, unsigned long long len, uint32_t n_tiles, const uint32_t *entry, uint32_t *exit_pos,
                              uint32_t *count, uint8_t *dirty)
 {
@@ -224,7 +181,6 @@ __global__ void k_frame_walk(const uint8_t *buf, unsigned long long len, uint32_
     unsigned long long pos = entry[tile];
     uint32_t n = 0;
     while (pos < end) {
-        frame_prefetch(buf, pos, len);
         pos = frame_next(buf, pos, len);
         n++;
     }
@@ -253,7 +209,6 @@ __global__ void k_frame_emit(const uint8_t *buf, unsigned long long len, uint32_
     unsigned long long pos = entry[tile];
     uint32_t at = base[tile];
     while (pos < end) {
-        frame_prefetch(buf, pos, len);
         offsets[at++] = (uint32_t)pos;
         pos = frame_next(buf, pos, len);
     }
