@@ -165,21 +165,13 @@ __host__ __device__ __forceinline__ unsigned long long hash64(const uint32_t *ke
     return h;
 }
 
-// Where a key lives in ITS OWN group table (and hot replica).  Nothing outside the library sees this value -- the sketch rows
-// and the box-wide owner of a key come from hash64, which the checker restates -- so narrow keys (one or two words: AS pairs,
-// ports) take a 6-instruction multiplicative mix instead of hash64's 40: the table index reads bits 32.., the replica index
-// bits 20.., both fed by every key bit.
+// Where a key lives in its own group table (and hot replica).  Nothing outside the library sees this value -- the sketch rows
+// and the box-wide owner of a key come from hash64 itself, which the checker restates -- so it could be cheaper than hash64 for
+// narrow keys; a 6-instruction multiplicative mix measured 3 % SLOWER than the 40-instruction hash64 on configs[1]
+// (profiles/r02/experiments), so it is hash64.
 template <int KW>
 __device__ __forceinline__ unsigned long long slot_hash(const uint32_t *key)
 {
-#ifdef FA_CHEAP_SLOT_HASH
-    if (KW <= 2) {
-        const uint32_t a = key[0] * 0x9E3779B1u;
-        const uint32_t b = KW == 2 ? key[KW == 2 ? 1 : 0] * 0x85EBCA77u : 0x27D4EB2Fu;
-        const uint32_t x = a ^ __funnelshift_l(b, b, 17);
-        return (unsigned long long)x * 0xD6E8FEB86659FD93ull;
-    }
-#endif
     return hash64<KW>(key);
 }
 
@@ -466,27 +458,6 @@ __device__ __forceinline__ void cms_add(const SubmitParams &p, unsigned long lon
     }
 }
 
-__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v)
-{
-    unsigned long long old;
-    asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
-    return old;
-}
-
-// the same update, returning the key's estimate right after it (min over the rows of the counters just written)
-__device__ __forceinline__ unsigned long long cms_add_estimate(const SubmitParams &p, unsigned long long h, unsigned long long weight)
-{
-    const uint32_t a = (uint32_t)h, b = (uint32_t)(h >> 32) | 1u;
-    const uint32_t mask = (1u << p.cms_wlog2) - 1u;
-    unsigned long long est = ~0ull;
-    for (uint32_t j = 0; j < p.cms_depth; j++) {
-        const uint32_t idx = (a + j * b) & mask;
-        const unsigned long long now = atom_add_u64(p.cms + ((size_t)j << p.cms_wlog2) + idx, weight) + weight;
-        est = now < est ? now : est;
-    }
-    return est;
-}
-
 // Bounded insert into the candidate table of FA_CFG_TOPK_ONLY: at most kCandProbes slots are looked at; a key that finds
 // neither itself nor a free slot is simply not a candidate (yet: its next flow tries again, and the table is pruned after
 // every submit).  KW == 4 layout (addresses).
@@ -600,14 +571,8 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         nokey++;
         return 0u;
     }
-#ifdef FA_CHEAP_SLOT_HASH
-    // narrow keys: the sketch hash only when a sketch is attached (uniform over the grid)
-    const unsigned long long hs = slot_hash<KW>(key);
-    const unsigned long long h = KW > 2 ? hash64<KW>(key) : hs;  // narrow keys: hash64 only inside the sketch branch below
-#else
     const unsigned long long h = hash64<KW>(key);
-    const unsigned long long hs = h;
-#endif
+    const unsigned long long hs = h;  // slot_hash<KW>(key)
     unsigned long long b = f.bytes, pk = f.packets;
     if (p.scale) {  // sum(Bytes*SamplingRate): viz-ch.json:74
         b *= f.sampling_rate;
@@ -622,41 +587,8 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
         // Two lookups decide a flow's path -- the CTA's replica (a key found there was a candidate when it got there, and
         // candidates only leave between launches) and the candidate table -- and their first probes are independent loads:
         // both are issued before either is looked at, so the common cases cost ONE L2 round trip, not two in a row.
-#ifdef FA_WARP_COMBINE
-        // (experiment, off: measured 1.5 % SLOWER on configs[2], profiles/r02/experiments)
-        // Heavy keys repeat inside a warp (the top address of a Zipf stream is 8 % of all flows): lanes holding the same key
-        // hand their sums to the lowest of them, which alone goes to memory -- the hottest replica sectors take a third of the
-        // atomics, and a load from a sector that atomics are queueing on waits behind them (ncu: profiles/r02).  Exact: lanes are
-        // grouped by both key halves; the sums are u64 adds in any order.
-        unsigned long long cnt = 1ull;
-        unsigned long long wsum = w;
-        {
-            const unsigned act = __activemask();
-            const unsigned lane = threadIdx.x & 31u;
-            const unsigned peers = __match_any_sync(act, klo) & __match_any_sync(act, khi);
-            const unsigned others = peers & ~(1u << lane);
-            const int rounds = __reduce_max_sync(act, (unsigned)__popc(others));
-            const unsigned long long b0 = b, pk0 = pk, w0 = w;
-            unsigned rest = others;
-            for (int i = 0; i < rounds; i++) {
-                const int src = rest ? __ffs((int)rest) - 1 : (int)lane;
-                const unsigned long long ob = __shfl_sync(act, b0, src), opk = __shfl_sync(act, pk0, src), ow = __shfl_sync(act, w0, src);
-                if (rest) {
-                    b += ob;
-                    pk += opk;
-                    wsum += ow;
-                    cnt++;
-                    rest &= rest - 1u;
-                }
-            }
-            if ((peers & ((1u << lane) - 1u)) != 0u) {  // a lower lane carries this key: nothing left to do here
-                total_w += w;
-                return (uint32_t)h;
-            }
-        }
-#else
+        // (lanes of a warp holding the same key combining before they go to memory measured 1.5 % slower: profiles/r02/experiments)
         const unsigned long long cnt = 1ull, wsum = w;
-#endif
         const bool keyed = p.slots && (klo & khi) != ~0ull;
         uint8_t *rep = p.hot_slots ? p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * ((size_t)p.hot_mask + 1u) * SlotLayout<4>::BYTES : nullptr;
         uint8_t *rs = nullptr, *cs = nullptr;
@@ -679,11 +611,6 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
             if (rep) done = hot_add_pending(rep, p.hot_mask, klo, khi, h, b, pk, cnt, wsum);
             if (!done) slot_add_pending(cs, b, pk, cnt, wsum);
         } else {
-#ifdef FA_ADMIT_ESTIMATE
-            // round-2 first version: admit on the estimate the update itself returns (four RETURNING atomics per flow)
-            const unsigned long long est = cms_add_estimate(p, h, wsum);
-            if (p.slots && est >= admit_bar) candidate_add(p, key, h, b, pk, cnt);
-#else
             // sample and hold (Estan & Varghese): the sketch takes the flow through fire-and-forget reductions, and the flow
             // makes its key a candidate with probability min(1, w / bar), bar = total weight / (64 K) -- at most 64 K
             // admissions are expected per launch whatever the number of keys, and a key that weighs several bars (every
@@ -695,7 +622,6 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
             const unsigned long long lo = (unsigned long long)u * admit_bar, hi = __umul64hi((unsigned long long)u, admit_bar);
             const bool admit = wsum >= admit_bar || hi < (wsum >> 32) || (hi == (wsum >> 32) && lo < (wsum << 32));   // u / 2^32 < w / bar
             if (p.slots && admit) candidate_add(p, key, h, b, pk, cnt);
-#endif
         }
         total_w += w;
         return (uint32_t)h;
@@ -706,11 +632,7 @@ __device__ __forceinline__ uint32_t aggregate_flow(const SubmitParams &p, const 
             done = hot_add<(KW <= 4 ? KW : 1)>(p.hot_slots + (size_t)(blockIdx.x & (kHotReplicas - 1u)) * kHotSlots * SlotLayout<(KW <= 4 ? KW : 1)>::BYTES, key, hs, b, pk);
         if (!done) table_add<KW, OUTLINE>(p, key, hs, b, pk, 1ull);
     }
-#ifdef FA_CHEAP_SLOT_HASH
-    if (p.cms) cms_add(p, KW > 2 ? h : hash64<KW>(key), f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
-#else
     if (p.cms) cms_add(p, h, f.bytes * f.sampling_rate);  // viz-ch.json:233 weight
-#endif
     return (uint32_t)(hs >> 32);
 }
 
