@@ -240,7 +240,9 @@ class FlowAgg:
         return b, o
 
     def submit(self, buf, offsets, framed=True, n_records=None, nbytes=None):
-        """Host buffers (numpy arrays or pinned torch tensors)."""
+        """Host buffers (numpy arrays or pinned torch tensors).  offsets=None (framed streams of at most max_batch_bytes): the record
+        boundaries are found on the GPU, and the call runs one behind -- it stages this buffer and launches the previously staged one;
+        stats / flush / sync finish the pending one (include/flowagg.h)."""
         n = (len(offsets) - 1) if offsets is not None and n_records is None else (n_records or 0)
         ln = nbytes if nbytes is not None else (buf.nbytes if isinstance(buf, np.ndarray) else buf.numel() * buf.element_size())
         self._check(self._L.fa_submit(self._h, _ptr(buf), ln, _ptr(offsets), n, FA_FRAMED if framed else 0), "fa_submit")
