@@ -47,6 +47,21 @@ def bench_config():
             "partitioning": "kafka partition = rank, one mocker instance (own seed, SequenceNum from 0) per partition"}
 
 
+def cut_pieces(offsets, limit):
+    """Cut a record stream into pieces of at most `limit` bytes at record boundaries (what a host that concatenated the Kafka values
+    knows without parsing anything).  offsets: n+1 ascending byte offsets; returns [(first_byte, end_byte)], covering
+    [offsets[0], offsets[n]) exactly once; a single record larger than the limit becomes a piece of its own."""
+    o = np.asarray(offsets, dtype=np.int64)
+    n = len(o) - 1
+    pieces, r0 = [], 0
+    while r0 < n:
+        r1 = int(np.searchsorted(o, o[r0] + limit, side="right")) - 1
+        r1 = min(max(r1, r0 + 1), n)
+        pieces.append((int(o[r0]), int(o[r1])))
+        r0 = r1
+    return pieces
+
+
 def mocker_cfg(fp, partition=0):
     # 250k flows/s of stream time: 100M flows span 400 s = two five-minute slots.  One mocker instance per Kafka
     # partition: its own random stream (seed) and its own SequenceNum counter from 0 (`var i uint32`, mocker/mocker.go:52,89)
@@ -566,13 +581,8 @@ def main():
         if not args.no_frame_leg:
             pieces = []
             for (hb, ho, n, nb) in hslabs:
-                o = ho.numpy().astype(np.int64)
-                r0 = 0
-                while r0 < n:
-                    r1 = int(np.searchsorted(o, o[r0] + (64 << 20), side="right")) - 1
-                    r1 = min(max(r1, r0 + 1), n)
-                    pieces.append((hb[int(o[r0]):int(o[r1])], int(o[r1] - o[r0])))
-                    r0 = r1
+                for (b0, b1) in cut_pieces(ho.numpy()[: n + 1], 64 << 20):
+                    pieces.append((hb[b0:b1], b1 - b0))
 
             def step_e2e_framed():
                 for (piece, nbytes) in pieces:

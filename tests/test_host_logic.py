@@ -258,3 +258,27 @@ def test_bench_gpu_arm_fails_loudly_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--flows", "100000"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_bench_cuts_the_stream_at_record_boundaries():
+    """bench.py's e2e leg without shipped offsets hands fa_submit(offsets = NULL) pieces of at most 64 MiB; every piece must start
+    and end on a record boundary and the pieces must tile the stream (include/flowagg.h)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(5)
+    sizes = rng.integers(0, 300, 20000)
+    sizes[[17, 4000]] = [5000, 1200]                       # two records larger than the limit
+    offs = np.concatenate([[7], 7 + np.cumsum(sizes)])     # a stream that does not start at byte 0
+    for limit in (1000, 4096, 1 << 20):
+        pieces = bench.cut_pieces(offs, limit)
+        assert pieces[0][0] == offs[0] and pieces[-1][1] == offs[-1]
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(pieces, pieces[1:]))            # contiguous, no overlap
+        bounds = set(offs.tolist())
+        assert all(b0 in bounds and b1 in bounds and b1 > b0 for b0, b1 in pieces)
+        big = {int(offs[i]) for i in range(len(sizes)) if sizes[i] > limit}
+        assert all(b1 - b0 <= limit or b0 in big for b0, b1 in pieces)                   # only a lone oversized record exceeds it
+    assert bench.cut_pieces(np.array([0]), 10) == []
